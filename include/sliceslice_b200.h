@@ -1,0 +1,191 @@
+/*
+ * sliceslice_b200.h -- C ABI of the B200-native single-pattern substring search.
+ *
+ * Drop-in boundary for ONE path of cloudflare/sliceslice-rs: the inner loop of
+ * sliceslice::x86::DynamicAvx2Searcher::search_in (Mula's two-anchor-byte filter
+ * + memcmp verify).  Every entry point cites the reference interface it replaces
+ * (file:line relative to the reference checkout).  Plain C types only: pointer +
+ * length pairs, SIZE_MAX for "not found" -- the same convention the reference's
+ * own FFI precedent uses (bench/sse4-strstr/src/wrapper.h:7, src/lib.rs:4-15).
+ *
+ * There is no CPU fallback: every search entry point runs hand-written sm_100a
+ * CUDA kernels and returns SS_B200_E_CUDA when no usable device is present.
+ *
+ * Error convention (the reference panics at construction only, src/x86.rs:300,
+ * :304, :473; search_in is infallible): no unwinding across the boundary; every
+ * function returns an int status and the Rust/C++/Python shims turn
+ * SS_B200_E_POSITION / SS_B200_E_EMPTY_NEEDLE into the reference's panics.
+ *
+ * Threading (reference: searchers are immutable plain data, Send + Sync,
+ * src/x86.rs:266-271): a const searcher / haystack handle may be used from any
+ * number of host threads concurrently; the synchronous calls keep their stream,
+ * workspace and result slot in thread-local storage.
+ */
+#ifndef SLICESLICE_B200_H
+#define SLICESLICE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_B200_ABI_VERSION 1
+
+/* "not found" for host-side offsets: usize::MAX / std::string::npos
+ * (bench/sse4-strstr/src/lib.rs:12-14). */
+#define SS_B200_NPOS ((size_t)-1)
+/* "not found" in a DEVICE result slot written by the *_async calls.  INT64_MAX so
+ * that a min-reduction over ranks works on both signed and unsigned views (NCCL /
+ * gloo have no bitwise OR; min over first offsets gives found AND the offset). */
+#define SS_B200_DEVICE_NONE 0x7FFFFFFFFFFFFFFFull
+
+enum ss_b200_status {
+    SS_B200_OK = 0,
+    SS_B200_E_POSITION = 1,     /* assert!(position < needle.size()) src/x86.rs:300; assert_eq!(position, 0) :473 */
+    SS_B200_E_EMPTY_NEEDLE = 2, /* Avx2Searcher::new(empty) panics, src/x86.rs:285,300 (strict ctors only) */
+    SS_B200_E_ARG = 3,          /* NULL handle / pointer */
+    SS_B200_E_CUDA = 4,         /* CUDA runtime error or no device; see ss_b200_last_error() */
+    SS_B200_E_NOMEM = 5
+};
+
+typedef struct ss_b200_searcher ss_b200_searcher; /* opaque, immutable after creation */
+typedef struct ss_b200_haystack ss_b200_haystack; /* opaque device-resident haystack   */
+typedef struct ss_b200_batch ss_b200_batch;       /* opaque device-resident word sets  */
+
+const char *ss_b200_strerror(int status);
+/* Thread-local detail string of the last SS_B200_E_CUDA on this thread. */
+const char *ss_b200_last_error(void);
+int ss_b200_abi_version(void);
+
+/* ------------------------------------------------------------------------- */
+/* Searcher construction.                                                     */
+
+/* DynamicAvx2Searcher::new(needle) -- src/x86.rs:454-459.
+ * position = len - 1 (wrapping; ignored for the empty needle). Never fails on
+ * the arguments; the empty needle is valid (variant N0, src/x86.rs:470). */
+int ss_b200_searcher_new(const uint8_t *needle, size_t len, ss_b200_searcher **out);
+
+/* DynamicAvx2Searcher::with_position(needle, position) -- src/x86.rs:468-493.
+ * len == 0: position ignored. len == 1: position must be 0 (:473).
+ * len >= 2: position < len (:300) else SS_B200_E_POSITION. */
+int ss_b200_searcher_with_position(const uint8_t *needle, size_t len, size_t position, ss_b200_searcher **out);
+
+/* Avx2Searcher::new / ::with_position -- src/x86.rs:282-287, :297-316.
+ * Same as above except that the empty needle is SS_B200_E_EMPTY_NEEDLE and a
+ * one-byte needle takes the generic two-anchor path with position 0. */
+int ss_b200_searcher_new_strict(const uint8_t *needle, size_t len, ss_b200_searcher **out);
+int ss_b200_searcher_with_position_strict(const uint8_t *needle, size_t len, size_t position,
+                                          ss_b200_searcher **out);
+
+void ss_b200_searcher_free(ss_b200_searcher *s); /* Drop */
+size_t ss_b200_searcher_needle_len(const ss_b200_searcher *s);
+size_t ss_b200_searcher_position(const ss_b200_searcher *s); /* private Searcher::position, src/lib.rs:289-293 */
+
+/* ------------------------------------------------------------------------- */
+/* Haystack residency (new concern: the reference borrows a host &[u8]).      */
+
+/* Copy `len` host bytes into HBM on the current device (owned by the handle). */
+int ss_b200_haystack_upload(const uint8_t *host, size_t len, ss_b200_haystack **out);
+/* Borrow `len` bytes already in device memory (any byte alignment). */
+int ss_b200_haystack_from_device(const void *dptr, size_t len, ss_b200_haystack **out);
+void ss_b200_haystack_free(ss_b200_haystack *h);
+size_t ss_b200_haystack_len(const ss_b200_haystack *h);
+const void *ss_b200_haystack_device_ptr(const ss_b200_haystack *h);
+
+/* ------------------------------------------------------------------------- */
+/* The hot call.                                                              */
+
+/* DynamicAvx2Searcher::search_in(&self, haystack) -> bool -- src/x86.rs:523-525
+ * (body :498-519 -> :356-376 -> src/lib.rs:253-287 -> :199-251).
+ * *found = 1/0. Semantics (k = needle len, n = haystack len): k==0 -> true;
+ * k==1 -> n>0 && byte present (src/lib.rs:130-136); n<k -> false;
+ * n==k -> haystack==needle (src/x86.rs:357-359); else any i in [0,n-k]. */
+int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haystack *h, uint8_t *found);
+
+/* Same scan, returning the index at which the reference's loop returns true --
+ * always the leftmost occurrence (src/lib.rs:263-274 ascending chunks, :221
+ * ascending bits, :242-244 first verified candidate) -- or SS_B200_NPOS.
+ * Mirrors avx2_strstr_v2's contract (bench/sse4-strstr/src/wrapper.cpp:18-28). */
+int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t *offset);
+
+/* search_in(&[u8]) with a HOST slice: the literal analogue of src/x86.rs:523.
+ * Streams the haystack to the device in chunks (pinned staging, copy/scan
+ * overlap) and scans it there; PCIe-bound by construction. */
+int ss_b200_search_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, uint8_t *found);
+int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, size_t *offset);
+
+/* Stream-ordered scan of device memory, no host synchronisation.
+ *   dptr, len     haystack bytes in device memory (any alignment)
+ *   base_offset   global coordinate of dptr[0]; added to the reported offset
+ *                 (shard r of a sharded haystack passes r * shard_len)
+ *   start_limit   number of start positions to test, counted from dptr[0]; pass
+ *                 SIZE_MAX for "all" (len - k + 1). A shard that carries a k-1
+ *                 byte right halo passes its own shard_len here so that
+ *                 positions owned by the next shard are not reported twice.
+ *   workspace     16 bytes of device memory, ZERO when the call is enqueued; the
+ *                 kernel leaves it zero again (self-resetting), so one
+ *                 cudaMemset at allocation time is enough for any number of
+ *                 searches issued back to back on one stream.
+ *   d_result      device (or mapped pinned host) uint64 slot: receives
+ *                 base_offset + first offset, or SS_B200_DEVICE_NONE.
+ *   stream        cudaStream_t (as void*); NULL = legacy default stream.
+ * This is the entry the roofline is measured on and the one the multi-GPU
+ * sharded mode calls before its min-allreduce. */
+int ss_b200_find_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base_offset,
+                                 size_t start_limit, void *workspace, uint64_t *d_result, void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* Batched modes (north-star "batched many-haystack mode"; workloads:
+ * bench/benches/i386.rs:118-131 short sweep, :246-257 all needles over one
+ * haystack).  Word sets are CSR: blob + (count+1) uint64 offsets, host memory. */
+
+int ss_b200_batch_create(const uint8_t *needle_blob, const uint64_t *needle_off, size_t n_needles,
+                         const uint8_t *hay_blob, const uint64_t *hay_off, size_t n_haystacks,
+                         ss_b200_batch **out);
+void ss_b200_batch_free(ss_b200_batch *b);
+
+/* Explicit pair list: pair p searches needle pair_needle[p] in haystack
+ * pair_hay[p] with DynamicAvx2Searcher::new semantics.  Outputs (host, either
+ * may be NULL): bitmap bit p (LSB-first in uint32 words) = search_in();
+ * offsets[p] = first offset or UINT64_MAX. */
+int ss_b200_batch_search_pairs(const ss_b200_batch *b, const uint32_t *pair_needle, const uint32_t *pair_hay,
+                               size_t n_pairs, uint32_t *bitmap, uint64_t *offsets);
+
+/* Triangular rule of the reference's short-haystack bench (needle i against
+ * every haystack j >= i, both sets being the same length-sorted word list):
+ * pair index p = i*W - i*(i-1)/2 + (j-i).  bitmap must hold ceil(W(W+1)/2 / 32)
+ * words.  *matches (nullable) receives the popcount. */
+int ss_b200_batch_search_triangular(const ss_b200_batch *b, uint32_t *bitmap, uint64_t *matches);
+
+/* Every needle of the batch over ONE long device-resident haystack in a single
+ * launch (each haystack tile is staged once and tested against the whole needle
+ * table).  offsets[w] = first offset or UINT64_MAX (host array, n_needles). */
+int ss_b200_batch_find_all_in(const ss_b200_batch *b, const ss_b200_haystack *h, uint64_t *offsets);
+
+/* ------------------------------------------------------------------------- */
+/* Synthetic inputs of BASELINE configs 2'/4/5, generated in HBM so that multi-
+ * GiB haystacks never cross PCIe.  Bit-identical CPU copies live in oracle/.  */
+
+/* dst[t] = byte(global_start + t), byte(i) = (splitmix64(seed ^ (i>>3)) >> 8(i&7)) & 0xFF, 0xFF -> 0x00 */
+int ss_b200_fill_random(void *d_dst, size_t len, uint64_t global_start, uint64_t seed, void *stream);
+/* dst[t] = src[(global_start + t) % src_len]; src is device memory. */
+int ss_b200_fill_tiled(void *d_dst, size_t len, uint64_t global_start, const void *d_src, size_t src_len,
+                       void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* Tuning / introspection (bench and tests; not part of the reference surface). */
+
+/* Kernel variant for the long scan: 0 = auto, 1 = direct 16-byte LDG,
+ * 2 = TMA bulk-staged shared-memory ring.  Process-wide. */
+int ss_b200_set_scan_variant(int variant);
+/* Overrides: ctas_per_sm (0 = auto), ... see DESIGN.md. */
+int ss_b200_set_scan_tuning(int ctas_per_sm, int unroll, int tile_kib, int stages);
+/* Number of kernel launches issued by this library in this process so far. */
+uint64_t ss_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLICESLICE_B200_H */

@@ -1,0 +1,361 @@
+"""sliceslice_rs_b200 -- B200-native single-pattern substring search behind the
+``DynamicAvx2Searcher`` surface of cloudflare/sliceslice-rs.
+
+This package is the Python host side ABOVE the C ABI (``include/sliceslice_b200.h``,
+implemented by ``libsliceslice_b200.so``: hand-written sm_100a CUDA, no torch types).
+It mirrors the reference's searcher interface for the one accelerated path::
+
+    reference (src/x86.rs)                              here
+    DynamicAvx2Searcher::new(needle)            ->  DynamicB200Searcher.new(needle)
+    DynamicAvx2Searcher::with_position(n, p)    ->  DynamicB200Searcher.with_position(n, p)
+    searcher.search_in(haystack) -> bool        ->  searcher.search_in(haystack) -> bool
+    Avx2Searcher::{new, with_position}          ->  B200Searcher.{new, with_position}
+    (panic at construction)                     ->  raises SearcherPanic
+
+plus ``find_in`` (the index at which the reference's scan returns true = leftmost
+occurrence).  PyTorch is used only as plumbing: device memory, streams, and
+``torch.distributed`` for the multi-GPU min-reduction (``sharded.py``).
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is usable,
+searches raise; nothing in this package imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+__all__ = ["DynamicB200Searcher", "B200Searcher", "DeviceHaystack", "SearcherPanic", "B200Error", "lib",
+           "NPOS", "DEVICE_NONE", "fill_random", "fill_tiled", "set_scan_variant", "set_scan_tuning",
+           "launch_count", "Batch"]
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libsliceslice_b200.so")
+NPOS = (1 << 64) - 1
+DEVICE_NONE = 0x7FFFFFFFFFFFFFFF
+OK, E_POSITION, E_EMPTY_NEEDLE, E_ARG, E_CUDA, E_NOMEM = range(6)
+
+_lib = None
+
+
+class SearcherPanic(AssertionError):
+    """The reference panics here (src/x86.rs:300 ``assert!(position < needle.size())``,
+    :473 ``assert_eq!(position, 0)``, :285 empty needle for ``Avx2Searcher``)."""
+
+
+class B200Error(RuntimeError):
+    """CUDA / argument failure reported by the C ABI (never raised by the reference)."""
+
+
+def lib() -> C.CDLL:
+    """Load libsliceslice_b200.so (built in-tree by ``python -m sliceslice_rs_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(f"{LIB_PATH} is missing: build it with `python -m sliceslice_rs_b200.build` "
+                        "(the CUDA path is the only path; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    sz, u64, vp, i32 = C.c_size_t, C.c_uint64, C.c_void_p, C.c_int
+    pp = C.POINTER(vp)
+    sig = {
+        "ss_b200_strerror": (C.c_char_p, [i32]),
+        "ss_b200_last_error": (C.c_char_p, []),
+        "ss_b200_abi_version": (i32, []),
+        "ss_b200_searcher_new": (i32, [vp, sz, pp]),
+        "ss_b200_searcher_with_position": (i32, [vp, sz, sz, pp]),
+        "ss_b200_searcher_new_strict": (i32, [vp, sz, pp]),
+        "ss_b200_searcher_with_position_strict": (i32, [vp, sz, sz, pp]),
+        "ss_b200_searcher_free": (None, [vp]),
+        "ss_b200_searcher_needle_len": (sz, [vp]),
+        "ss_b200_searcher_position": (sz, [vp]),
+        "ss_b200_haystack_upload": (i32, [vp, sz, pp]),
+        "ss_b200_haystack_from_device": (i32, [vp, sz, pp]),
+        "ss_b200_haystack_free": (None, [vp]),
+        "ss_b200_haystack_len": (sz, [vp]),
+        "ss_b200_haystack_device_ptr": (vp, [vp]),
+        "ss_b200_search_in": (i32, [vp, vp, C.POINTER(C.c_uint8)]),
+        "ss_b200_find_in": (i32, [vp, vp, C.POINTER(sz)]),
+        "ss_b200_search_in_host": (i32, [vp, vp, sz, C.POINTER(C.c_uint8)]),
+        "ss_b200_find_in_host": (i32, [vp, vp, sz, C.POINTER(sz)]),
+        "ss_b200_find_in_device_async": (i32, [vp, vp, sz, u64, sz, vp, vp, vp]),
+        "ss_b200_batch_create": (i32, [vp, vp, sz, vp, vp, sz, pp]),
+        "ss_b200_batch_free": (None, [vp]),
+        "ss_b200_batch_search_pairs": (i32, [vp, vp, vp, sz, vp, vp]),
+        "ss_b200_batch_search_triangular": (i32, [vp, vp, C.POINTER(u64)]),
+        "ss_b200_batch_find_all_in": (i32, [vp, vp, vp]),
+        "ss_b200_fill_random": (i32, [vp, sz, u64, u64, vp]),
+        "ss_b200_fill_tiled": (i32, [vp, sz, u64, vp, sz, vp]),
+        "ss_b200_set_scan_variant": (i32, [i32]),
+        "ss_b200_set_scan_tuning": (i32, [i32, i32, i32, i32]),
+        "ss_b200_launch_count": (u64, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)  # AttributeError here == header/library mismatch: fail loudly
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+DECLARED_SYMBOLS = None  # filled lazily by tests from include/sliceslice_b200.h
+
+
+def _check(rc: int) -> None:
+    if rc == OK:
+        return
+    if rc in (E_POSITION, E_EMPTY_NEEDLE):
+        raise SearcherPanic(lib().ss_b200_strerror(rc).decode())
+    detail = lib().ss_b200_last_error().decode() if rc in (E_CUDA, E_NOMEM) else ""
+    raise B200Error(f"{lib().ss_b200_strerror(rc).decode()} {detail}".strip())
+
+
+def _host_view(b):
+    """bytes-like / numpy -> (address, length, keepalive) without copying when possible."""
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b).view(np.uint8).reshape(-1)
+        return a.ctypes.data, a.size, a
+    mv = memoryview(b)
+    if mv.nbytes == 0:
+        z = np.zeros(1, np.uint8)
+        return z.ctypes.data, 0, z
+    a = np.frombuffer(mv, dtype=np.uint8)
+    return a.ctypes.data, a.size, (a, b)
+
+
+def _is_torch_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+class DeviceHaystack:
+    """A haystack resident in HBM (``ss_b200_haystack``): uploaded (owned) or borrowed from a
+    CUDA uint8 tensor / raw device pointer."""
+
+    def __init__(self, handle, keepalive=None):
+        self._h = handle
+        self._keep = keepalive
+
+    @classmethod
+    def upload(cls, data) -> "DeviceHaystack":
+        addr, n, keep = _host_view(data)
+        h = C.c_void_p()
+        _check(lib().ss_b200_haystack_upload(addr, n, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_tensor(cls, t) -> "DeviceHaystack":
+        if not t.is_cuda or t.dtype.itemsize != 1 or not t.is_contiguous():
+            raise B200Error("from_tensor needs a contiguous 1-byte CUDA tensor")
+        h = C.c_void_p()
+        _check(lib().ss_b200_haystack_from_device(t.data_ptr(), t.numel(), C.byref(h)))
+        return cls(h, keepalive=t)
+
+    @classmethod
+    def from_pointer(cls, dptr: int, length: int, keepalive=None) -> "DeviceHaystack":
+        h = C.c_void_p()
+        _check(lib().ss_b200_haystack_from_device(dptr, length, C.byref(h)))
+        return cls(h, keepalive)
+
+    def __len__(self) -> int:
+        return lib().ss_b200_haystack_len(self._h)
+
+    @property
+    def device_ptr(self) -> int:
+        return lib().ss_b200_haystack_device_ptr(self._h) or 0
+
+    def close(self) -> None:
+        if self._h:
+            lib().ss_b200_haystack_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _SearcherBase:
+    _STRICT = False
+
+    def __init__(self, handle, needle: bytes):
+        self._s = handle
+        self._needle = needle
+
+    # -- construction: same names, argument meaning and failure behaviour as the reference ----
+    @classmethod
+    def new(cls, needle):
+        """``::new(needle)``: second anchor = last byte (src/x86.rs:454-459 / :282-287)."""
+        nb = bytes(needle)
+        addr, n, keep = _host_view(nb)
+        h = C.c_void_p()
+        fn = lib().ss_b200_searcher_new_strict if cls._STRICT else lib().ss_b200_searcher_new
+        _check(fn(addr, n, C.byref(h)))
+        return cls(h, nb)
+
+    @classmethod
+    def with_position(cls, needle, position: int):
+        """``::with_position(needle, position)`` (src/x86.rs:468-493 / :297-316)."""
+        nb = bytes(needle)
+        if position < 0:
+            raise SearcherPanic("position must be an unsigned index")
+        addr, n, keep = _host_view(nb)
+        h = C.c_void_p()
+        fn = lib().ss_b200_searcher_with_position_strict if cls._STRICT else lib().ss_b200_searcher_with_position
+        _check(fn(addr, n, position, C.byref(h)))
+        return cls(h, nb)
+
+    # -- accessors (the reference's private Searcher trait, src/lib.rs:289-293) ---------------
+    @property
+    def needle(self) -> bytes:
+        return self._needle
+
+    @property
+    def position(self) -> int:
+        return lib().ss_b200_searcher_position(self._s)
+
+    # -- the hot call ------------------------------------------------------------------------
+    def find_in(self, haystack) -> Optional[int]:
+        """Index at which the reference's scan returns true (leftmost occurrence) or None."""
+        out = C.c_size_t(0)
+        if isinstance(haystack, DeviceHaystack):
+            _check(lib().ss_b200_find_in(self._s, haystack._h, C.byref(out)))
+        elif _is_torch_tensor(haystack) and haystack.is_cuda:
+            hs = DeviceHaystack.from_tensor(haystack)
+            _check(lib().ss_b200_find_in(self._s, hs._h, C.byref(out)))
+            hs.close()
+        else:
+            if _is_torch_tensor(haystack):
+                if not haystack.is_contiguous() or haystack.dtype.itemsize != 1:
+                    raise B200Error("host tensor must be contiguous and 1 byte per element")
+                addr, n, keep = haystack.data_ptr(), haystack.numel(), haystack
+            else:
+                addr, n, keep = _host_view(haystack)
+            _check(lib().ss_b200_find_in_host(self._s, addr, n, C.byref(out)))
+        return None if out.value == NPOS else out.value
+
+    def search_in(self, haystack) -> bool:
+        """``search_in(&self, haystack: &[u8]) -> bool`` (src/x86.rs:523-525)."""
+        return self.find_in(haystack) is not None
+
+    inlined_search_in = search_in  # src/x86.rs:496-519; inlining is a Rust codegen concern only
+
+    def find_in_async(self, hay, result, workspace, base_offset: int = 0, start_limit: Optional[int] = None,
+                      stream=None) -> None:
+        """Stream-ordered scan of a CUDA uint8 tensor (``ss_b200_find_in_device_async``).
+
+        ``result``: 1-element int64/uint64 CUDA tensor receiving base_offset + first offset or
+        DEVICE_NONE; ``workspace``: >= 16 zero bytes of CUDA memory (kept zero by the kernel)."""
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(hay.device)
+        sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        lim = NPOS if start_limit is None else int(start_limit)
+        _check(lib().ss_b200_find_in_device_async(self._s, hay.data_ptr(), hay.numel(), int(base_offset), lim,
+                                                  workspace.data_ptr(), result.data_ptr(), sp))
+
+    def close(self) -> None:
+        if self._s:
+            lib().ss_b200_searcher_free(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DynamicB200Searcher(_SearcherBase):
+    """Drop-in for ``sliceslice::x86::DynamicAvx2Searcher`` (src/x86.rs:405-526)."""
+    _STRICT = False
+
+
+class B200Searcher(_SearcherBase):
+    """Drop-in for ``sliceslice::x86::Avx2Searcher`` (src/x86.rs:266-383): empty needle panics."""
+    _STRICT = True
+
+
+class Batch:
+    """Device-resident needle and haystack sets for the batched modes (``ss_b200_batch``)."""
+
+    def __init__(self, needles, haystacks):
+        self.n_needles, self.n_haystacks = len(needles), len(haystacks)
+        nb, no = _csr(needles)
+        hb, ho = _csr(haystacks)
+        h = C.c_void_p()
+        _check(lib().ss_b200_batch_create(nb.ctypes.data, no.ctypes.data, len(needles), hb.ctypes.data,
+                                          ho.ctypes.data, len(haystacks), C.byref(h)))
+        self._b = h
+
+    def search_pairs(self, pair_needle, pair_hay, want_offsets: bool = True):
+        pn = np.ascontiguousarray(pair_needle, np.uint32)
+        ph = np.ascontiguousarray(pair_hay, np.uint32)
+        bm = np.zeros((pn.size + 31) // 32, np.uint32)
+        off = np.empty(pn.size, np.uint64) if want_offsets else None
+        _check(lib().ss_b200_batch_search_pairs(self._b, pn.ctypes.data, ph.ctypes.data, pn.size, bm.ctypes.data,
+                                                off.ctypes.data if want_offsets else None))
+        return bm, off
+
+    def search_triangular(self):
+        w = self.n_needles
+        npairs = w * (w + 1) // 2
+        bm = np.zeros((npairs + 31) // 32, np.uint32)
+        m = C.c_uint64(0)
+        _check(lib().ss_b200_batch_search_triangular(self._b, bm.ctypes.data, C.byref(m)))
+        return bm, m.value
+
+    def find_all_in(self, haystack: DeviceHaystack):
+        out = np.empty(self.n_needles, np.uint64)
+        _check(lib().ss_b200_batch_find_all_in(self._b, haystack._h, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self._b:
+            lib().ss_b200_batch_free(self._b)
+            self._b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _csr(items):
+    off = np.zeros(len(items) + 1, np.uint64)
+    if len(items):
+        off[1:] = np.cumsum([len(x) for x in items], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(bytes(x) for x in items), np.uint8) if int(off[-1]) else np.zeros(1, np.uint8)
+    return np.ascontiguousarray(blob), off
+
+
+def fill_random(t, global_start: int, seed: int, stream=None) -> None:
+    """Fill a CUDA uint8 tensor with the splitmix64 byte stream of BASELINE configs 4/5."""
+    import torch
+
+    sp = (stream or torch.cuda.current_stream(t.device)).cuda_stream
+    _check(lib().ss_b200_fill_random(t.data_ptr(), t.numel(), global_start, seed, sp))
+
+
+def fill_tiled(t, global_start: int, src, stream=None) -> None:
+    """t[i] = src[(global_start + i) % len(src)] for CUDA uint8 tensors (config 2')."""
+    import torch
+
+    sp = (stream or torch.cuda.current_stream(t.device)).cuda_stream
+    _check(lib().ss_b200_fill_tiled(t.data_ptr(), t.numel(), global_start, src.data_ptr(), src.numel(), sp))
+
+
+def set_scan_variant(variant: int) -> None:
+    _check(lib().ss_b200_set_scan_variant(variant))
+
+
+def set_scan_tuning(ctas_per_sm: int = 0, unroll: int = 0, tile_kib: int = 0, stages: int = 0) -> None:
+    _check(lib().ss_b200_set_scan_tuning(ctas_per_sm, unroll, tile_kib, stages))
+
+
+def launch_count() -> int:
+    return lib().ss_b200_launch_count()

@@ -1,0 +1,590 @@
+// capi.cu -- the extern "C" boundary declared in include/sliceslice_b200.h.
+//
+// Host runtime around the sm_100a kernels: opaque searcher / haystack handles,
+// thread-local stream + self-resetting workspace + mapped result slot for the
+// synchronous calls, the chunked host->device streaming path, and the
+// stream-ordered entry used for roofline measurement and the multi-GPU shards.
+// No CPU search path exists in this library: without a device every search
+// returns SS_B200_E_CUDA.
+#include "../../include/sliceslice_b200.h"
+#include "ss_host.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------
+// errors
+
+static thread_local std::string t_last_error;
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    t_last_error = buf;
+    return e == cudaErrorMemoryAllocation ? SS_B200_E_NOMEM : SS_B200_E_CUDA;
+}
+#define SS_CUDA(call)                                                                                                \
+    do {                                                                                                             \
+        cudaError_t e__ = (call);                                                                                    \
+        if (e__ != cudaSuccess)                                                                                      \
+            return cuda_fail(e__, #call);                                                                            \
+    } while (0)
+
+int ss_capi_cuda_fail(cudaError_t e, const char *what) { return cuda_fail(e, what); }
+
+extern "C" const char *ss_b200_strerror(int status)
+{
+    switch (status) {
+    case SS_B200_OK: return "ok";
+    case SS_B200_E_POSITION: return "position is not a valid index for the needle";
+    case SS_B200_E_EMPTY_NEEDLE: return "needle is empty";
+    case SS_B200_E_ARG: return "invalid argument";
+    case SS_B200_E_CUDA: return "CUDA error or no usable device";
+    case SS_B200_E_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+extern "C" const char *ss_b200_last_error(void) { return t_last_error.c_str(); }
+extern "C" int ss_b200_abi_version(void) { return SS_B200_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------
+// process-wide tuning + per-device facts
+
+static SsScanTuning g_tuning;
+static std::mutex g_dev_mutex;
+static std::map<int, SsDeviceInfo> g_devs;
+
+static int device_info(SsDeviceInfo &out)
+{
+    int dev = -1;
+    SS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    auto it = g_devs.find(dev);
+    if (it == g_devs.end()) {
+        SsDeviceInfo d;
+        d.device = dev;
+        SS_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        SS_CUDA(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        SS_CUDA(cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        const char *v = getenv("SS_B200_LONG_VARIANT");
+        d.auto_long_variant = (v && atoi(v) == 1) ? 1 : 2;
+        it = g_devs.emplace(dev, d).first;
+    }
+    out = it->second;
+    return SS_B200_OK;
+}
+
+int ss_capi_device_info(SsDeviceInfo &out) { return device_info(out); }
+
+extern "C" int ss_b200_set_scan_variant(int variant)
+{
+    if (variant < 0 || variant > 2)
+        return SS_B200_E_ARG;
+    g_tuning.variant = variant;
+    return SS_B200_OK;
+}
+extern "C" int ss_b200_set_scan_tuning(int ctas_per_sm, int unroll, int tile_kib, int stages)
+{
+    g_tuning.ctas_per_sm = ctas_per_sm;
+    g_tuning.unroll = unroll;
+    g_tuning.tile_kib = tile_kib;
+    g_tuning.stages = stages;
+    return SS_B200_OK;
+}
+extern "C" uint64_t ss_b200_launch_count(void) { return ss_host_launch_count(); }
+
+// ---------------------------------------------------------------------------------------------
+// handles
+
+struct ss_b200_searcher {
+    std::vector<uint8_t> needle;
+    size_t position = 0;
+    bool strict = false; // Avx2Searcher flavour: one-byte needles take the two-anchor path too
+    // device copies of long needles, one per device that has searched with this handle
+    mutable std::mutex mu;
+    mutable std::map<int, uint8_t *> dev_needle;
+};
+
+struct ss_b200_haystack {
+    const uint8_t *dptr = nullptr;
+    size_t len = 0;
+    bool owned = false;
+    int device = -1;
+};
+
+static int make_searcher(const uint8_t *needle, size_t len, size_t position, bool have_position, bool strict,
+                         ss_b200_searcher **out)
+{
+    if (!out || (len && !needle))
+        return SS_B200_E_ARG;
+    *out = nullptr;
+    if (!have_position)
+        position = len - 1; // wrapping_sub(1), src/x86.rs:285,457
+    if (strict) {
+        // Avx2Searcher::with_position, src/x86.rs:297-305
+        if (len == 0)
+            return SS_B200_E_EMPTY_NEEDLE; // "position < size" cannot hold
+        if (position >= len)
+            return SS_B200_E_POSITION;
+    } else {
+        // DynamicAvx2Searcher::with_position, src/x86.rs:468-493
+        if (len == 1 && position != 0)
+            return SS_B200_E_POSITION; // assert_eq!(position, 0) :473
+        if (len >= 2 && position >= len)
+            return SS_B200_E_POSITION; // :300
+        if (len == 0)
+            position = 0; // N0: position ignored (:470)
+    }
+    ss_b200_searcher *s = new (std::nothrow) ss_b200_searcher();
+    if (!s)
+        return SS_B200_E_NOMEM;
+    s->needle.assign(needle, needle + len);
+    s->position = position;
+    s->strict = strict;
+    *out = s;
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_searcher_new(const uint8_t *needle, size_t len, ss_b200_searcher **out)
+{
+    return make_searcher(needle, len, 0, false, false, out);
+}
+extern "C" int ss_b200_searcher_with_position(const uint8_t *needle, size_t len, size_t position,
+                                              ss_b200_searcher **out)
+{
+    return make_searcher(needle, len, position, true, false, out);
+}
+extern "C" int ss_b200_searcher_new_strict(const uint8_t *needle, size_t len, ss_b200_searcher **out)
+{
+    return make_searcher(needle, len, 0, false, true, out);
+}
+extern "C" int ss_b200_searcher_with_position_strict(const uint8_t *needle, size_t len, size_t position,
+                                                     ss_b200_searcher **out)
+{
+    return make_searcher(needle, len, position, true, true, out);
+}
+extern "C" void ss_b200_searcher_free(ss_b200_searcher *s)
+{
+    if (!s)
+        return;
+    for (auto &kv : s->dev_needle)
+        cudaFree(kv.second);
+    delete s;
+}
+extern "C" size_t ss_b200_searcher_needle_len(const ss_b200_searcher *s) { return s ? s->needle.size() : 0; }
+extern "C" size_t ss_b200_searcher_position(const ss_b200_searcher *s) { return s ? s->position : 0; }
+
+extern "C" int ss_b200_haystack_upload(const uint8_t *host, size_t len, ss_b200_haystack **out)
+{
+    if (!out || (len && !host))
+        return SS_B200_E_ARG;
+    *out = nullptr;
+    int dev = -1;
+    SS_CUDA(cudaGetDevice(&dev));
+    uint8_t *d = nullptr;
+    SS_CUDA(cudaMalloc(&d, ((len + 15) & ~(size_t)15) + 16));
+    if (len) {
+        cudaError_t e = cudaMemcpy(d, host, len, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return cuda_fail(e, "cudaMemcpy(haystack)");
+        }
+    }
+    ss_b200_haystack *h = new (std::nothrow) ss_b200_haystack();
+    if (!h) {
+        cudaFree(d);
+        return SS_B200_E_NOMEM;
+    }
+    h->dptr = d;
+    h->len = len;
+    h->owned = true;
+    h->device = dev;
+    *out = h;
+    return SS_B200_OK;
+}
+extern "C" int ss_b200_haystack_from_device(const void *dptr, size_t len, ss_b200_haystack **out)
+{
+    if (!out || (len && !dptr))
+        return SS_B200_E_ARG;
+    ss_b200_haystack *h = new (std::nothrow) ss_b200_haystack();
+    if (!h)
+        return SS_B200_E_NOMEM;
+    h->dptr = (const uint8_t *)dptr;
+    h->len = len;
+    h->owned = false;
+    *out = h;
+    return SS_B200_OK;
+}
+extern "C" void ss_b200_haystack_free(ss_b200_haystack *h)
+{
+    if (!h)
+        return;
+    if (h->owned && h->dptr)
+        cudaFree((void *)h->dptr);
+    delete h;
+}
+extern "C" size_t ss_b200_haystack_len(const ss_b200_haystack *h) { return h ? h->len : 0; }
+extern "C" const void *ss_b200_haystack_device_ptr(const ss_b200_haystack *h) { return h ? h->dptr : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// per-thread, per-device context for the synchronous calls
+
+struct HostSlot {
+    volatile unsigned long long value;
+    volatile unsigned long long seq;
+};
+
+struct ThreadCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    SsWorkspace *ws = nullptr;
+    HostSlot *slot = nullptr;   // pinned + mapped
+    HostSlot *slot_dev = nullptr; // device view of the same memory
+    unsigned long long seq = 0;
+    // host-path staging (lazily sized)
+    static const int NBUF = 3;
+    uint8_t *dbuf[NBUF] = {nullptr, nullptr, nullptr};
+    size_t dbuf_cap = 0;
+    cudaEvent_t copied[NBUF] = {nullptr, nullptr, nullptr};
+    cudaEvent_t scanned[NBUF] = {nullptr, nullptr, nullptr};
+    unsigned long long *chunk_results = nullptr; // pinned + mapped, one per in-flight chunk
+    unsigned long long *chunk_results_dev = nullptr;
+    size_t chunk_results_cap = 0;
+};
+
+static thread_local std::map<int, ThreadCtx> t_ctx;
+
+static int get_ctx(ThreadCtx **out)
+{
+    int dev = -1;
+    SS_CUDA(cudaGetDevice(&dev));
+    ThreadCtx &c = t_ctx[dev];
+    if (c.device < 0) {
+        SS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        SS_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        SS_CUDA(cudaMalloc(&c.ws, sizeof(SsWorkspace)));
+        SS_CUDA(cudaMemset(c.ws, 0, sizeof(SsWorkspace)));
+        SS_CUDA(cudaHostAlloc((void **)&c.slot, sizeof(HostSlot), cudaHostAllocMapped));
+        c.slot->value = 0;
+        c.slot->seq = 0;
+        SS_CUDA(cudaHostGetDevicePointer((void **)&c.slot_dev, (void *)c.slot, 0));
+        SS_CUDA(cudaDeviceSynchronize());
+        c.device = dev;
+    }
+    *out = &c;
+    return SS_B200_OK;
+}
+
+static int needle_on_device(const ss_b200_searcher *s, int dev, const uint8_t **out)
+{
+    std::lock_guard<std::mutex> lk(s->mu);
+    auto it = s->dev_needle.find(dev);
+    if (it == s->dev_needle.end()) {
+        uint8_t *d = nullptr;
+        SS_CUDA(cudaMalloc(&d, s->needle.size() + 16));
+        cudaError_t e = cudaMemcpy(d, s->needle.data(), s->needle.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return cuda_fail(e, "cudaMemcpy(needle)");
+        }
+        it = s->dev_needle.emplace(dev, d).first;
+    }
+    *out = it->second;
+    return SS_B200_OK;
+}
+
+// Build the kernel arguments for one scan (k >= 1, len >= k).
+static int build_args(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base, size_t start_limit,
+                      int dev, ScanArgs &a)
+{
+    memset(&a, 0, sizeof a);
+    const size_t k = s->needle.size();
+    a.hay = (const uint8_t *)dptr;
+    a.n = len;
+    a.base = base;
+    a.k = (uint32_t)k;
+    a.pos = (uint32_t)s->position;
+    const uint8_t f = s->needle[0], l = s->needle[s->position];
+    a.f4 = 0x01010101u * f;
+    a.l4 = 0x01010101u * l;
+    if (k <= SS_INLINE_NEEDLE_MAX) {
+        memcpy(a.needle_inline, s->needle.data(), k);
+    } else {
+        int rc = needle_on_device(s, dev, &a.needle_g);
+        if (rc != SS_B200_OK)
+            return rc;
+    }
+    ss_host_scan_geometry(a, start_limit);
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len,
+                                            uint64_t base_offset, size_t start_limit, void *workspace,
+                                            uint64_t *d_result, void *stream)
+{
+    if (!s || !d_result || !workspace || (len && !dptr))
+        return SS_B200_E_ARG;
+    const size_t k = s->needle.size();
+    if (k > 0xFFFFFFFFull)
+        return SS_B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    // trivial outcomes are still delivered in stream order through the result slot
+    if (k == 0 || len < k || start_limit == 0) {
+        // N0 => true at 0 (src/x86.rs:500); n < k => false (src/x86.rs:357-359, src/lib.rs:131-133)
+        const unsigned long long v = (k == 0) ? (unsigned long long)base_offset : SS_NONE_U64;
+        SS_CUDA(cudaMemcpyAsync(d_result, &v, sizeof v, cudaMemcpyHostToDevice, st));
+        return SS_B200_OK;
+    }
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    ScanArgs a;
+    rc = build_args(s, dptr, len, base_offset, start_limit, dev.device, a);
+    if (rc != SS_B200_OK)
+        return rc;
+    a.ws = (SsWorkspace *)workspace;
+    a.out = (unsigned long long *)d_result;
+    a.out_seq = nullptr;
+    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
+    return SS_B200_OK;
+}
+
+// One synchronous scan of device memory through the thread's context.
+static int find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset)
+{
+    const size_t k = s->needle.size();
+    if (k == 0) { // DynamicAvx2Searcher::N0 => true, even for an empty haystack (src/x86.rs:470,500)
+        *offset = 0;
+        return SS_B200_OK;
+    }
+    if (len < k) { // src/x86.rs:357-359 (haystack == needle is false); k==1: src/lib.rs:131-133
+        *offset = SS_B200_NPOS;
+        return SS_B200_OK;
+    }
+    if (k > 0xFFFFFFFFull)
+        return SS_B200_E_ARG;
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    ThreadCtx *c = nullptr;
+    rc = get_ctx(&c);
+    if (rc != SS_B200_OK)
+        return rc;
+    ScanArgs a;
+    rc = build_args(s, dptr, len, 0, (size_t)-1, dev.device, a);
+    if (rc != SS_B200_OK)
+        return rc;
+    a.ws = c->ws;
+    a.out = (unsigned long long *)&c->slot_dev->value;
+    a.out_seq = (unsigned long long *)&c->slot_dev->seq;
+    a.seq = ++c->seq;
+    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, c->stream));
+    // spin on the mapped sequence word; fall back to the stream status every so often
+    unsigned spins = 0;
+    while (c->slot->seq != a.seq) {
+        if ((++spins & 0x3FF) == 0) {
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e == cudaSuccess)
+                break; // kernel retired: the mapped writes are visible now
+            if (e != cudaErrorNotReady)
+                return cuda_fail(e, "scan kernel");
+        }
+    }
+    if (c->slot->seq != a.seq) {
+        SS_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->slot->seq != a.seq) {
+            t_last_error = "scan kernel retired without publishing a result";
+            return SS_B200_E_CUDA;
+        }
+    }
+    const unsigned long long v = c->slot->value;
+    *offset = (v == SS_NONE_U64) ? SS_B200_NPOS : (size_t)v;
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t *offset)
+{
+    if (!s || !h || !offset)
+        return SS_B200_E_ARG;
+    return find_device_sync(s, h->dptr, h->len, offset);
+}
+
+extern "C" int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haystack *h, uint8_t *found)
+{
+    if (!s || !h || !found)
+        return SS_B200_E_ARG;
+    size_t off = SS_B200_NPOS;
+    int rc = find_device_sync(s, h->dptr, h->len, &off);
+    if (rc == SS_B200_OK)
+        *found = (off != SS_B200_NPOS) ? 1 : 0;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-resident haystack: chunked upload overlapped with the scan (PCIe-bound by construction)
+
+static size_t host_chunk_bytes()
+{
+    const char *v = getenv("SS_B200_HOST_CHUNK_MIB");
+    size_t mib = v ? (size_t)atoll(v) : 0;
+    if (mib == 0)
+        mib = 64;
+    return mib << 20;
+}
+
+extern "C" int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, size_t *offset)
+{
+    if (!s || !offset || (len && !host))
+        return SS_B200_E_ARG;
+    const size_t k = s->needle.size();
+    if (k == 0) {
+        *offset = 0;
+        return SS_B200_OK;
+    }
+    if (len < k) {
+        *offset = SS_B200_NPOS;
+        return SS_B200_OK;
+    }
+    if (k > 0xFFFFFFFFull)
+        return SS_B200_E_ARG;
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    ThreadCtx *c = nullptr;
+    rc = get_ctx(&c);
+    if (rc != SS_B200_OK)
+        return rc;
+
+    const size_t halo = k - 1;
+    size_t chunk = host_chunk_bytes();
+    if (chunk > len)
+        chunk = (len + 15) & ~(size_t)15;
+    const size_t end_total = len - k + 1;
+    const size_t n_chunks = (end_total + chunk - 1) / chunk;
+    const size_t need = chunk + halo + 32;
+    if (c->dbuf_cap < need) {
+        for (int b = 0; b < ThreadCtx::NBUF; b++) {
+            if (c->dbuf[b])
+                cudaFree(c->dbuf[b]);
+            c->dbuf[b] = nullptr;
+            SS_CUDA(cudaMalloc(&c->dbuf[b], need));
+            if (!c->copied[b]) {
+                SS_CUDA(cudaEventCreateWithFlags(&c->copied[b], cudaEventDisableTiming));
+                SS_CUDA(cudaEventCreateWithFlags(&c->scanned[b], cudaEventDisableTiming));
+            }
+        }
+        c->dbuf_cap = need;
+    }
+    if (c->chunk_results_cap < n_chunks) {
+        if (c->chunk_results)
+            cudaFreeHost(c->chunk_results);
+        c->chunk_results = nullptr;
+        SS_CUDA(cudaHostAlloc((void **)&c->chunk_results, n_chunks * sizeof(unsigned long long), cudaHostAllocMapped));
+        SS_CUDA(cudaHostGetDevicePointer((void **)&c->chunk_results_dev, c->chunk_results, 0));
+        c->chunk_results_cap = n_chunks;
+    }
+    for (size_t i = 0; i < n_chunks; i++)
+        c->chunk_results[i] = ~0ull; // "not produced yet"
+
+    ScanArgs proto;
+    rc = build_args(s, c->dbuf[0], k, 0, (size_t)-1, dev.device, proto); // needle fields; geometry redone per chunk
+    if (rc != SS_B200_OK)
+        return rc;
+
+    size_t submitted = 0;
+    unsigned long long best = SS_NONE_U64;
+    for (size_t i = 0; i < n_chunks; i++) {
+        // the reference returns at the first match (src/lib.rs:242-244): stop feeding once an
+        // already-finished chunk has reported one
+        bool hit = false;
+        for (size_t j = 0; j < submitted; j++) {
+            const unsigned long long v = ((volatile unsigned long long *)c->chunk_results)[j];
+            if (v != ~0ull && v != SS_NONE_U64) {
+                hit = true;
+                break;
+            }
+        }
+        if (hit)
+            break;
+        const int b = (int)(i % ThreadCtx::NBUF);
+        const size_t off = i * chunk;
+        size_t bytes = chunk + halo;
+        if (off + bytes > len)
+            bytes = len - off;
+        if (i >= (size_t)ThreadCtx::NBUF)
+            SS_CUDA(cudaStreamWaitEvent(c->copy_stream, c->scanned[b], 0));
+        SS_CUDA(cudaMemcpyAsync(c->dbuf[b], host + off, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        SS_CUDA(cudaEventRecord(c->copied[b], c->copy_stream));
+        SS_CUDA(cudaStreamWaitEvent(c->stream, c->copied[b], 0));
+        ScanArgs a = proto;
+        a.hay = c->dbuf[b];
+        a.n = bytes;
+        a.base = off;
+        ss_host_scan_geometry(a, chunk);
+        a.ws = c->ws;
+        a.out = c->chunk_results_dev + i;
+        a.out_seq = nullptr;
+        SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, c->stream));
+        SS_CUDA(cudaEventRecord(c->scanned[b], c->stream));
+        submitted++;
+    }
+    SS_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t j = 0; j < submitted; j++) {
+        const unsigned long long v = c->chunk_results[j];
+        if (v != ~0ull && v < best)
+            best = v;
+    }
+    *offset = (best == SS_NONE_U64) ? SS_B200_NPOS : (size_t)best;
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_search_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, uint8_t *found)
+{
+    if (!found)
+        return SS_B200_E_ARG;
+    size_t off = SS_B200_NPOS;
+    int rc = ss_b200_find_in_host(s, host, len, &off);
+    if (rc == SS_B200_OK)
+        *found = (off != SS_B200_NPOS) ? 1 : 0;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generators
+
+extern "C" int ss_b200_fill_random(void *d_dst, size_t len, uint64_t global_start, uint64_t seed, void *stream)
+{
+    if (len && !d_dst)
+        return SS_B200_E_ARG;
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    SS_CUDA(ss_host_fill_random(d_dst, len, global_start, seed, dev.sm_count, (cudaStream_t)stream));
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_fill_tiled(void *d_dst, size_t len, uint64_t global_start, const void *d_src, size_t src_len,
+                                  void *stream)
+{
+    if ((len && !d_dst) || !d_src || src_len == 0)
+        return SS_B200_E_ARG;
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    SS_CUDA(ss_host_fill_tiled(d_dst, len, global_start, d_src, src_len, dev.sm_count, (cudaStream_t)stream));
+    return SS_B200_OK;
+}

@@ -1,0 +1,255 @@
+// scan_long.cuh -- K1, the long-haystack scan (the roofline kernel).
+//
+// GPU re-expression of vector_search_in / vector_search_in_chunk
+// (reference src/lib.rs:253-287, :199-251): the haystack is cut into 16-byte
+// chunks counted from the 16-byte-aligned address at or below hay[0]; every lane
+// tests the 16 start positions of one chunk per step with the SWAR two-anchor
+// filter (ss_device.cuh), a warp ballot collapses the per-lane candidate flags,
+// and only warps that saw a candidate enter the exact decode + memcmp verify.
+// The leftmost match is kept with one atomicMax on ~offset; tiles are visited in
+// ascending order and a tile whose first position lies beyond the current best
+// is skipped (the reference's early return, src/lib.rs:242-244, made parallel).
+//
+// Two data paths, same arithmetic:
+//   scan_ldg_kernel  coalesced 16-byte LDG straight from HBM/L2 (variant 1)
+//   scan_tma_kernel  1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a
+//                    shared-memory ring guarded by mbarriers; consumers read the
+//                    tile with 16-byte LDS (variant 2)
+#pragma once
+#include "ss_device.cuh"
+
+#define SS_LDG_THREADS 256
+#define SS_TMA_CONSUMER_WARPS 8
+#define SS_TMA_THREADS ((SS_TMA_CONSUMER_WARPS + 1) * 32)
+#define SS_TMA_HALO_MAX 2048 // bytes of right halo a TMA stage can carry
+
+// ------------------------------------------------------------------------------------------
+// Variant 1: direct LDG.  CTA tile = WARPS * U * 32 chunks; warp w owns a contiguous run of
+// U*32 chunks of it; tiles are dealt blocked-cyclically so the grid sweeps the haystack as a
+// moving band (good for early exit and DRAM page locality).
+//   R   = pos % 16   (compile time: byte shift of the second anchor stream)
+//   QZ  = pos / 16 == 0  (the B window starts in the lane's own chunk)
+//   K1  = one-byte needle (memchr path of src/lib.rs:130-136): first anchor only
+//   U   = chunks per lane per step (independent 16-byte loads in flight)
+// One warp step: U*32 chunks starting at chunk `cw` (lane l takes cw + l + 32u).
+// CLAMP=false is the interior fast path (every load provably in range: plain base+immediate
+// addressing); CLAMP=true clamps each chunk index to the last loadable chunk (tail tiles).
+// Returns true when the early-exit test says this CTA can stop.
+template <int R, bool QZ, bool K1, int U, bool CLAMP>
+__device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restrict__ chunks, unsigned long long cw,
+                                         int lane, uint32_t f4, uint32_t l4)
+{
+    // early exit: nothing at or right of this warp's first position can beat the current best
+    const unsigned long long key = ld_relaxed_u64(&a.ws->key);
+    const unsigned long long last = a.last_chunk;
+    const unsigned long long c0 = cw + lane;
+    const uint4 *p = chunks + c0;
+    const uint4 *pq = p + a.q;
+
+    uint4 av[U], lo[U], hi[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (CLAMP) {
+            const unsigned long long c = c0 + u * 32;
+            av[u] = ldg16(chunks + (c < last ? c : last));
+        } else {
+            av[u] = ldg16(p + u * 32);
+        }
+    }
+    if (!K1) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (CLAMP) {
+                const unsigned long long c = c0 + u * 32 + a.q;
+                lo[u] = QZ ? av[u] : ldg16(chunks + (c < last ? c : last));
+                hi[u] = (R > 0) ? ldg16(chunks + (c + 1 < last ? c + 1 : last)) : lo[u];
+            } else {
+                lo[u] = QZ ? av[u] : ldg16(pq + u * 32);
+                hi[u] = (R > 0) ? ldg16(pq + u * 32 + 1) : lo[u];
+            }
+        }
+    }
+    if (key) {
+        const long long first_pos = (long long)(cw * 16ull) - (long long)a.head;
+        if (first_pos > (long long)~key)
+            return true;
+    }
+    uint32_t fl[U];
+    uint32_t any = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        fl[u] = chunk_flag<R, K1>(av[u], lo[u], hi[u], f4, l4);
+        any |= fl[u];
+    }
+    if (__any_sync(0xFFFFFFFFu, any != 0)) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned long long c = c0 + u * 32;
+            if (fl[u] && (!CLAMP || c < a.n_chunks))
+                verify_chunk<R, K1>(a, av[u], lo[u], hi[u], c);
+        }
+    }
+    return false;
+}
+
+template <int R, bool QZ, bool K1, int U>
+__global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_constant__ ScanArgs a)
+{
+    constexpr int WARPS = SS_LDG_THREADS / 32;
+    constexpr unsigned long long CTA_CHUNKS = (unsigned long long)WARPS * U * 32;
+    const uint4 *chunks = reinterpret_cast<const uint4 *>(a.hay - a.head);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned long long n_tiles = (a.n_chunks + CTA_CHUNKS - 1) / CTA_CHUNKS;
+    // tiles [0, n_interior): every chunk holds start positions and every load (incl. the
+    // second-anchor window at +q, +q+1) stays at or below last_chunk
+    unsigned long long n_interior = a.n_chunks / CTA_CHUNKS;
+    {
+        const unsigned long long lim = (a.last_chunk >= a.q) ? (a.last_chunk - a.q) / CTA_CHUNKS : 0;
+        if (lim < n_interior)
+            n_interior = lim;
+    }
+    const uint32_t f4 = a.f4, l4 = a.l4;
+
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
+        bool stop;
+        if (tile < n_interior) {
+            stop = ldg_step<R, QZ, K1, U, false>(a, chunks, cw, lane, f4, l4);
+        } else {
+            if (cw >= a.n_chunks)
+                continue; // this warp's run holds no start position (warp-uniform)
+            stop = ldg_step<R, QZ, K1, U, true>(a, chunks, cw, lane, f4, l4);
+        }
+        if (stop)
+            break; // every later tile of this CTA is further right still
+    }
+    scan_finish(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 2: TMA-staged.  One producer warp (one elected lane) streams tiles of TILE bytes plus
+// a right halo of 16*(q + (R>0)) bytes into a ring of `stages` shared-memory buffers with
+// cp.async.bulk; SS_TMA_CONSUMER_WARPS warps wait on the stage's "full" mbarrier, run the same
+// SWAR filter out of shared memory, and release the stage through its "empty" mbarrier.
+// Dynamic smem layout: [stages][stage_stride] data, then full[stages], empty[stages] mbarriers,
+// then one uint32 "valid" word per stage (0 = producer stopped: early exit or end of work).
+template <int R, bool QZ, bool K1, int TILE>
+__global__ void __launch_bounds__(SS_TMA_THREADS) scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages,
+                                                                  uint32_t stage_stride)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int CW = SS_TMA_CONSUMER_WARPS;
+    constexpr int TILE_CHUNKS = TILE / 16;
+    constexpr int WARP_CHUNKS = TILE_CHUNKS / CW; // contiguous run per consumer warp
+    constexpr int U = 4;
+    static_assert(WARP_CHUNKS % (32 * U) == 0, "tile must split into whole 32*U-chunk steps per warp");
+
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)stages * stage_stride);
+    uint64_t *empty = full + stages;
+    volatile uint32_t *valid = reinterpret_cast<volatile uint32_t *>(empty + stages);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned long long n_tiles = (a.n_chunks + TILE_CHUNKS - 1) / TILE_CHUNKS;
+    const uint32_t halo = K1 ? 0u : 16u * (a.q + (R > 0 ? 1u : 0u));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == CW) {
+        // ===== producer =====
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_first();
+            const uint8_t *gbase = a.hay - a.head;
+            const unsigned long long data_bytes = (a.last_chunk + 1) * 16ull; // loadable bytes from gbase
+            int s = 0;
+            uint32_t ph = 0;
+            unsigned long long tile = blockIdx.x;
+            for (;; tile += gridDim.x) {
+                mbar_wait(&empty[s], ph ^ 1);
+                bool go = tile < n_tiles;
+                if (go) {
+                    const unsigned long long key = ld_relaxed_u64(&a.ws->key);
+                    const long long first_pos = (long long)(tile * (unsigned long long)TILE) - (long long)a.head;
+                    if (key && first_pos > (long long)~key)
+                        go = false;
+                }
+                if (!go) {
+                    valid[s] = 0;
+                    mbar_arrive(&full[s]); // release: consumers see valid == 0 and leave
+                    break;
+                }
+                const unsigned long long off = tile * (unsigned long long)TILE;
+                unsigned long long bytes = (unsigned long long)TILE + halo;
+                if (off + bytes > data_bytes)
+                    bytes = data_bytes - off; // still a multiple of 16
+                valid[s] = 1;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)bytes);
+                tma_load_1d(smem + (size_t)s * stage_stride, gbase + off, (uint32_t)bytes, &full[s], policy);
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===== consumers =====
+        const uint32_t f4 = a.f4, l4 = a.l4;
+        const uint32_t qb = a.q * 16u;
+        int s = 0;
+        uint32_t ph = 0;
+        for (unsigned long long tile = blockIdx.x;; tile += gridDim.x) {
+            mbar_wait(&full[s], ph);
+            if (valid[s] == 0)
+                break;
+            const uint8_t *st = smem + (size_t)s * stage_stride;
+            const unsigned long long tile_c0 = tile * (unsigned long long)TILE_CHUNKS;
+#pragma unroll 1
+            for (int step = 0; step < WARP_CHUNKS / (32 * U); step++) {
+                const uint32_t lc0 = (uint32_t)warp * WARP_CHUNKS + step * (32 * U) + lane; // chunk within tile
+                uint4 av[U], lo[U], hi[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    av[u] = lds16(st + (lc0 + u * 32) * 16u);
+                if (!K1) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const uint32_t b = (lc0 + u * 32) * 16u + qb;
+                        lo[u] = QZ ? av[u] : lds16(st + b);
+                        hi[u] = (R > 0) ? lds16(st + b + 16u) : lo[u];
+                    }
+                }
+                uint32_t fl[U];
+                uint32_t any = 0;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    fl[u] = chunk_flag<R, K1>(av[u], lo[u], hi[u], f4, l4);
+                    any |= fl[u];
+                }
+                if (__any_sync(0xFFFFFFFFu, any != 0)) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const unsigned long long c = tile_c0 + lc0 + u * 32;
+                        if (fl[u] && c < a.n_chunks)
+                            verify_chunk<R, K1>(a, av[u], lo[u], hi[u], c);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&empty[s]);
+            if (++s == stages) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+    scan_finish(a);
+}

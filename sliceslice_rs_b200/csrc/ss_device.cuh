@@ -1,0 +1,260 @@
+// ss_device.cuh -- shared device-side definitions for the sm_100a scan kernels.
+//
+// Replaces, on the GPU, the instruction mix of the reference's AVX2 `Vector`
+// impl (src/x86.rs:202-235: vmovdqu / vpcmpeqb / vpand / vpmovmskb) and the
+// block loop of src/lib.rs:199-287.  GPUs have no byte-compare/movemask, so the
+// two-anchor filter is expressed as 32-bit SWAR over 16-byte chunks:
+//     x = (A ^ splat(first)) | (B ^ splat(last))      B = haystack shifted by `position`
+//     any zero byte in x  <=>  candidate              (x - 0x01010101) & ~x & 0x80808080
+// The SWAR test is exact as an "any candidate in this word" test (false positives
+// only above a true zero byte), so no candidate is ever missed; exact per-byte
+// decode and the memcmp verify (src/lib.rs:216-244) run on the rare hit path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SS_INLINE_NEEDLE_MAX 64
+#define SS_NONE_U64 0x7FFFFFFFFFFFFFFFull // SS_B200_DEVICE_NONE
+
+// 16-byte self-resetting per-stream workspace.  `key` holds ~(smallest local
+// offset found so far) so that ZERO means "nothing found": a zero-filled
+// allocation is a valid initial state and the last CTA restores it.
+struct SsWorkspace {
+    unsigned long long key;
+    unsigned int done;
+    unsigned int pad;
+};
+
+struct ScanArgs {
+    const uint8_t *hay;          // haystack bytes (any alignment), device memory
+    unsigned long long n;        // haystack length
+    unsigned long long end;      // number of start positions to test (>= 1, <= n - k + 1)
+    unsigned long long base;     // global coordinate of hay[0]
+    unsigned long long n_chunks; // 16-byte chunks (from the aligned-down base) holding >= 1 start position
+    unsigned long long last_chunk; // index of the chunk holding hay[n-1]; loads are clamped to it
+    const uint8_t *needle_g;     // device copy of the needle when k > SS_INLINE_NEEDLE_MAX, else nullptr
+    SsWorkspace *ws;
+    unsigned long long *out;     // result slot: base + first offset, or SS_NONE_U64
+    unsigned long long *out_seq; // optional (mapped host) sequence slot written after *out
+    unsigned long long seq;
+    uint32_t k;    // needle length (>= 1)
+    uint32_t pos;  // second anchor index (`position`), < k
+    uint32_t q;    // pos / 16
+    uint32_t head; // hay - align_down(hay, 16), 0..15
+    uint32_t f4;   // needle[0] splatted x4
+    uint32_t l4;   // needle[pos] splatted x4
+    uint8_t needle_inline[SS_INLINE_NEEDLE_MAX];
+};
+
+__device__ __forceinline__ uint4 ldg16(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint4 ldg16_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// SWAR "some byte of x is zero" accumulator term (bit 7 of each byte, plus
+// possible false positives above a true zero byte).
+__device__ __forceinline__ uint32_t swar_zero_term(uint32_t x) { return (x - 0x01010101u) & ~x; }
+
+// Exact: 0x80 in every byte of x that is zero, 0 elsewhere.
+__device__ __forceinline__ uint32_t swar_zero_exact(uint32_t x)
+{
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+
+// Word j (0..3) of the 16 bytes that start at byte R of the 32-byte window lo||hi.
+template <int R>
+__device__ __forceinline__ uint32_t window_word(const uint4 &lo, const uint4 &hi, int j)
+{
+    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    constexpr int ws = R / 4;
+    constexpr int bs = (R % 4) * 8;
+    if (bs == 0)
+        return v[ws + j];
+    return __funnelshift_r(v[ws + j], v[ws + j + 1], bs);
+}
+
+// Candidate test for the 16 start positions of one chunk.
+//   a  : haystack bytes [16c, 16c+16)
+//   lo : haystack bytes [16(c+q), +16), hi: the next 16 (only read when R > 0)
+// Returns non-zero iff some position MAY satisfy hay[i]==first && hay[i+pos]==last.
+template <int R, bool K1>
+__device__ __forceinline__ uint32_t chunk_flag(const uint4 &a, const uint4 &lo, const uint4 &hi, uint32_t f4,
+                                               uint32_t l4)
+{
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t x = aw[j] ^ f4;
+        if (!K1)
+            x |= window_word<R>(lo, hi, j) ^ l4;
+        acc |= swar_zero_term(x);
+    }
+    return acc & 0x80808080u;
+}
+
+// memcmp of needle[1..k) against h[1..k) -- the verify of src/lib.rs:216-244
+// (byte 0 is already proven equal by the filter).
+__device__ __forceinline__ bool needle_tail_equal(const ScanArgs &a, const uint8_t *h)
+{
+    const uint32_t k = a.k;
+    if (k <= SS_INLINE_NEEDLE_MAX) {
+        for (uint32_t j = 1; j < k; j++)
+            if (__ldg(h + j) != a.needle_inline[j])
+                return false;
+        return true;
+    }
+    const uint8_t *nd = a.needle_g;
+    uint32_t j = 1;
+    // byte steps until h + j is 8-byte aligned, then 8 bytes of haystack per step
+    for (; j < k && ((reinterpret_cast<uintptr_t>(h + j)) & 7); j++)
+        if (__ldg(h + j) != __ldg(nd + j))
+            return false;
+    for (; j + 8 <= k; j += 8) {
+        unsigned long long hv = __ldg(reinterpret_cast<const unsigned long long *>(h + j));
+        unsigned long long nv = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            nv |= (unsigned long long)__ldg(nd + j + t) << (8 * t);
+        if (hv != nv)
+            return false;
+    }
+    for (; j < k; j++)
+        if (__ldg(h + j) != __ldg(nd + j))
+            return false;
+    return true;
+}
+
+// Hit path for one chunk whose SWAR flag fired: exact per-byte decode in ascending
+// position order (the ctz loop of src/lib.rs:220-248), range check, verify, publish.
+template <int R, bool K1>
+__device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 lo, uint4 hi, unsigned long long chunk)
+{
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+    const long long p0 = (long long)(chunk * 16ull) - (long long)a.head; // position of byte 0 of the chunk
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t x = aw[j] ^ a.f4;
+        if (!K1)
+            x |= window_word<R>(lo, hi, j) ^ a.l4;
+        uint32_t z = swar_zero_exact(x);
+        while (z) {
+            const int bit = __ffs((int)z) - 1;
+            z &= z - 1;
+            const long long i = p0 + 4 * j + (bit >> 3);
+            if (i < 0 || (unsigned long long)i >= a.end)
+                continue;
+            if (K1 || needle_tail_equal(a, a.hay + i)) {
+                atomicMax(&a.ws->key, ~(unsigned long long)i);
+                __threadfence();
+                return; // ascending order: later positions of this chunk cannot be smaller
+            }
+        }
+    }
+}
+
+// Grid-wide epilogue: the last CTA to finish publishes the result and restores the
+// workspace to all-zero so the next launch on this stream needs no memset.
+__device__ __forceinline__ void scan_finish(const ScanArgs &a)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(&a.ws->done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence();
+            const unsigned long long key = atomicExch(&a.ws->key, 0ull);
+            a.ws->done = 0;
+            const unsigned long long r = key ? (a.base + ~key) : SS_NONE_U64;
+            if (a.out_seq) {
+                // mapped pinned host slot: value first, then the sequence number the host spins on
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.out), "l"(r) : "memory");
+                __threadfence_system();
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.out_seq), "l"(a.seq) : "memory");
+            } else {
+                *a.out = r;
+            }
+        }
+    }
+}
+
+// ---- mbarrier / TMA (cp.async.bulk) PTX wrappers -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+// Requires 16-byte aligned src, dst and size.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                            uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, "
+                 "[%3], %4;" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 lds16(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(smem_u32(p)));
+    return r;
+}

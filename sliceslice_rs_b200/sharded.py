@@ -1,0 +1,105 @@
+"""Multi-GPU modes: one process per GPU, ``torch.distributed`` as plumbing.
+
+The path shards embarrassingly (start positions are independent, reference
+src/lib.rs:263-274 carries no state between chunks except the early return):
+
+* **one huge haystack** -- rank r owns the start positions of the contiguous byte range
+  ``[r*S, (r+1)*S)`` and holds ``S + k - 1`` bytes (right halo only).  Each rank runs the K1
+  scan with ``base_offset = r*S`` and ``start_limit = S``; the only exchange is an 8-byte
+  ``all_reduce(MIN)`` over the global first offsets (``DEVICE_NONE`` = INT64_MAX = not found),
+  which yields both the OR of the per-shard match flags and the exact leftmost offset.
+  NCCL has no bitwise OR (nccl.h: sum, prod, max, min, avg), hence MIN.
+* **many haystacks** -- haystack index ranges per rank (length-balanced), needles replicated;
+  per-haystack uint8 flags reduced with ``all_reduce(MAX)``.
+
+The partition arithmetic and the reductions are backend-agnostic (tested with gloo,
+world_size 2, on CPU); the scans themselves only run on CUDA.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+from . import DEVICE_NONE
+
+
+def shard_bounds(total_len: int, k: int, world: int, rank: int, align: int = 16) -> Tuple[int, int, int]:
+    """Contiguous shard of a haystack of ``total_len`` bytes for a needle of length ``k``.
+
+    Returns ``(start, owned, span)``: the shard owns start positions ``[start, start+owned)``
+    and must hold bytes ``[start, start+span)`` (owned + right halo of k-1, clipped).
+    ``owned`` is a multiple of ``align`` except for the last non-empty shard."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    per = -(-total_len // world)
+    per = -(-per // align) * align
+    start = min(rank * per, total_len)
+    owned = min(per, total_len - start)
+    span = min(owned + max(k, 1) - 1, total_len - start)
+    return start, owned, span
+
+
+def partition_by_length(lengths: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Split haystack indices into ``world`` contiguous ranges with balanced total bytes."""
+    n = len(lengths)
+    total = sum(lengths)
+    out, i, acc = [], 0, 0
+    for r in range(world):
+        target = total * (r + 1) / world
+        j = i
+        while j < n and (acc + lengths[j] <= target or r == world - 1):
+            acc += lengths[j]
+            j += 1
+        out.append((i, j))
+        i = j
+    return out
+
+
+def reduce_first_offset(local, group=None) -> Optional[int]:
+    """all_reduce(MIN) over per-rank global first offsets (1-element int64 tensor holding the
+    offset or DEVICE_NONE).  Returns the global leftmost offset or None; `local` is updated."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(local, op=dist.ReduceOp.MIN, group=group)
+    v = int(local.item())
+    return None if v == DEVICE_NONE else v
+
+
+def reduce_flags(flags, group=None):
+    """all_reduce(MAX) over per-haystack uint8 match flags (each haystack lives on one rank)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+    return flags
+
+
+class ShardedSearch:
+    """Rank-local state for repeated searches over one sharded haystack.
+
+    ``shard``: CUDA uint8 tensor holding this rank's bytes (owned + halo);
+    ``start``/``owned``: from :func:`shard_bounds`."""
+
+    def __init__(self, shard, start: int, owned: int, group=None):
+        import torch
+
+        self.shard, self.start, self.owned, self.group = shard, start, owned, group
+        self.workspace = torch.zeros(16, dtype=torch.uint8, device=shard.device)
+        self.result = torch.full((1,), DEVICE_NONE, dtype=torch.int64, device=shard.device)
+
+    def find_async(self, searcher, stream=None):
+        """Enqueue scan + MIN-allreduce on the current stream; returns the device result tensor."""
+        import torch.distributed as dist
+
+        searcher.find_in_async(self.shard, self.result, self.workspace, base_offset=self.start,
+                               start_limit=self.owned, stream=stream)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.result, op=dist.ReduceOp.MIN, group=self.group)
+        return self.result
+
+    def find(self, searcher) -> Optional[int]:
+        v = int(self.find_async(searcher).item())
+        return None if v == DEVICE_NONE else v
+
+    def search(self, searcher) -> bool:
+        return self.find(searcher) is not None
