@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- haystack GB/s scanned on the i386 long-haystack workload (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU; driver launches this for N > 1)
+
+Workload (SURVEY.md section 8d, config 2'): data/i386.txt tiled to --gib GiB per GPU (default 8),
+needle 'ipsum' built with DynamicAvx2Searcher::new semantics (second anchor = last byte).  The
+needle is absent, so every step scans the whole haystack: algorithmic bytes = haystack bytes, 1
+byte read per haystack byte, 0 written.  The haystack is 60x larger than L2, so no L2 flush is
+needed between steps.  One step = one search = one kernel launch per GPU.
+
+  value      whole-job GB/s with the haystack resident in HBM (ss_b200_find_in_device_async on
+             the torch stream, CUDA events, max over ranks).  N > 1: rank r owns the start
+             positions of global bytes [r*S, (r+1)*S) plus a k-1 byte right halo, and every step
+             ends with the 8-byte NCCL all_reduce(MIN) of the first offsets (weak scaling).
+  e2e        the same search through ss_b200_find_in_host on a pinned HOST buffer: chunked
+             host->device copies, scans and the result read are all inside the timed region.
+  roofline   achieved HBM GB/s of the scan kernel (per-launch CUDA events) / measured copy peak.
+  cpu_baseline  the C restatement of DynamicAvx2Searcher (oracle/, the checker) timed on this
+             box's host cores over a bounded sample of the same workload (rank 0, N = 1).
+
+--impl reference times that CPU restatement with all host threads (rank 0 only).
+The product path never touches oracle/: it is imported only inside cpu_baseline()/reference_arm().
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "haystack GB/s scanned (i386 long-haystack)"
+UNIT = "GB/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--gib", type=float, default=8.0, help="haystack GiB per GPU")
+    p.add_argument("--needle", default="ipsum")
+    p.add_argument("--variant", type=int, default=0, help="0 auto, 1 LDG, 2 TMA")
+    p.add_argument("--tuning", default="", help="ctas_per_sm,unroll,tile_kib,stages")
+    p.add_argument("--e2e-steps", type=int, default=5)
+    p.add_argument("--e2e-gib", type=float, default=0.0, help="host haystack GiB per GPU (0 = same as --gib)")
+    p.add_argument("--cpu-sample-gib", type=float, default=1.0)
+    p.add_argument("--no-extras", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def load_i386() -> bytes:
+    with open(os.path.join(ROOT, "data", "i386.txt"), "rb") as f:
+        return f.read()
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy read+write)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic():
+    """DRAM bytes per launch of the scan kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                    pw.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (the only places that touch oracle/)
+
+
+def tiled_host(i386: bytes, length: int, global_start: int = 0):
+    import numpy as np
+
+    src = np.frombuffer(i386, np.uint8)
+    m = src.size
+    out = np.empty(length, np.uint8)
+    ph = global_start % m
+    first = min(length, m - ph)
+    out[:first] = src[ph:ph + first]
+    pos = first
+    while pos < length:
+        c = min(m, length - pos)
+        out[pos:pos + c] = src[:c]
+        pos += c
+    return out
+
+
+def cpu_baseline(i386: bytes, needle: bytes, sample_gib: float):
+    """DynamicAvx2Searcher restatement (oracle/sliceslice_oracle.c), 1 thread = the reference's own
+    execution model (no threads in src/), plus an all-cores figure for context."""
+    import oracle
+
+    n = int(sample_gib * (1 << 30))
+    hay = tiled_host(i386, n)
+    cores = len(os.sched_getaffinity(0))
+    assert oracle.find(hay[: 4 << 20], needle) is None
+    times = []
+    t_end = time.perf_counter() + 12.0
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        r = oracle.find(hay, needle)
+        times.append(time.perf_counter() - t0)
+        assert r is None
+    one = n / statistics.median(times) / 1e9
+    mt = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        r = oracle.find(hay, needle, threads=cores)
+        mt.append(time.perf_counter() - t0)
+        assert r is None
+    return {"value": round(one, 3), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"i386.txt tiled to {sample_gib:g} GiB in host DRAM, needle {needle!r} absent, "
+                      f"{len(times)} full scans, median; C restatement of DynamicAvx2Searcher (gcc -O3 -mavx2)",
+            "all_cores": {"value": round(n / min(mt) / 1e9, 3), "cores": cores}}
+
+
+def reference_arm(args):
+    """The reference's CPU implementation of the path (restated in C; rustc is not in the image) with
+    all host threads, on a bounded sample of the same workload.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import oracle
+
+    i386 = load_i386()
+    needle = args.needle.encode()
+    cores = len(os.sched_getaffinity(0))
+    gib = min(args.gib, 4.0)
+    n = int(gib * (1 << 30))
+    hay = tiled_host(i386, n)
+    for _ in range(max(args.warmup, 1)):
+        assert oracle.find(hay, needle, threads=cores) is None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.find(hay, needle, threads=cores)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt / 1e9
+    sample = (f"i386.txt tiled to {gib:g} GiB in host DRAM (bounded sample of the {args.gib:g} GiB/GPU workload), "
+              f"needle {args.needle!r} absent, {cores} threads over contiguous slices with a k-1 halo")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "i386 long-haystack (i386.txt tiled), needle 'ipsum', CPU AVX2 reference path",
+                   "haystack_bytes": n},
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+
+
+def extras_single_gpu(ss, torch, i386: bytes, hay, args):
+    """Context numbers outside the headline timed region (rank 0, N = 1): other absent needles on the
+    same haystack, and the literal config 2 (4 585 words x 857 KB i386.txt; L2-resident, launch-bound,
+    so no HBM fraction is claimed for it)."""
+    out = {}
+    ws = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    res = torch.zeros(1, dtype=torch.int64, device="cuda")
+    sweep = {}
+    for nd in ("zq", "ipsumdol", "consecteturadipi", "\xff"):
+        s = ss.DynamicB200Searcher.new(nd.encode("latin-1"))
+        for _ in range(2):
+            s.find_in_async(hay, res, ws)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            s.find_in_async(hay, res, ws)
+        e1.record()
+        torch.cuda.synchronize()
+        assert int(res.item()) == ss.DEVICE_NONE
+        sweep[repr(nd.encode("latin-1"))] = round(hay.numel() * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
+    out["absent_needle_sweep_gbs"] = sweep
+
+    with open(os.path.join(ROOT, "data", "words.txt"), "rb") as f:
+        words = [w for w in f.read().split(b"\n") if w]
+    hs = ss.DeviceHaystack.upload(i386)
+    searchers = [ss.DynamicB200Searcher.new(w) for w in words]
+    best = None
+    for it in range(4):
+        t0 = time.perf_counter()
+        offs = [s.find_in(hs) for s in searchers]
+        dt = time.perf_counter() - t0
+        if it:
+            best = dt if best is None else min(best, dt)
+    assert sum(offs) == 809985317
+    batch = ss.Batch(words, [])
+    bbest = None
+    for it in range(4):
+        t0 = time.perf_counter()
+        o2 = batch.find_all_in(hs)
+        dt = time.perf_counter() - t0
+        if it:
+            bbest = dt if bbest is None else min(bbest, dt)
+    assert int(o2.sum()) == 809985317
+    out["config2_literal"] = {
+        "what": "all 4585 words.txt needles over the 857425-byte i386.txt, device-resident, host wall clock",
+        "api_faithful_ms_per_iteration": round(best * 1e3, 3),
+        "batched_single_launch_ms_per_iteration": round(bbest * 1e3, 3),
+        "examined_bytes": 810016020, "sum_first_offsets": 809985317,
+        "readme_i7_6700_ms": 35.181,
+        "note": "L2-resident and early-exit: launch-latency-bound, no HBM-fraction claim",
+    }
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import sliceslice_rs_b200 as ss
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA path is the only path (no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    ss.lib()
+    ss.set_scan_variant(args.variant)
+    if args.tuning:
+        ss.set_scan_tuning(*[int(x) for x in args.tuning.split(",")])
+
+    i386 = load_i386()
+    needle = args.needle.encode()
+    k = len(needle)
+    assert (i386 + i386).find(needle) < 0, "the bench needle must be absent from i386.txt and the tiling seam"
+    S = int(args.gib * (1 << 30))  # start positions owned per rank
+    total = S * world
+    start = rank * S
+    span = min(S + k - 1, total - start)  # owned + right halo (the last rank has none)
+    owned = S if rank < world - 1 else span - k + 1
+
+    src = torch.frombuffer(bytearray(i386), dtype=torch.uint8).cuda()
+    shard = torch.empty(span, dtype=torch.uint8, device="cuda")
+    ss.fill_tiled(shard, start, src)
+    searcher = ss.DynamicB200Searcher.new(needle)
+    ws = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    result = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(ev_a=None, ev_b=None):
+        if ev_a is not None:
+            ev_a.record()
+        searcher.find_in_async(shard, result, ws, base_offset=start, start_limit=owned)
+        if ev_b is not None:
+            ev_b.record()
+        if world > 1:
+            dist.all_reduce(result, op=dist.ReduceOp.MIN)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    assert int(result.item()) == ss.DEVICE_NONE, "needle must be absent"
+
+    K = args.steps
+    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ss.launch_count()
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(ka[i], kb[i])
+    e1.record()
+    barrier()
+    launches = ss.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    assert int(result.item()) == ss.DEVICE_NONE
+
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = [a.elapsed_time(b) for a, b in zip(ka, kb)]
+    tt = torch.tensor([ms_total, sum(kern_ms) / K, float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, kern_avg_ms, launches = float(mx[0]), float(mx[1]), int(sm[2])
+    else:
+        kern_avg_ms = float(tt[1])
+    value = total * K / (ms_total * 1e-3) / 1e9
+    peak, peak_src = peak_hbm()
+    kern_bytes = owned + k - 1 if owned else 0  # bytes one launch must examine (not found => all of them)
+    achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9
+    traffic = committed_traffic()
+
+    # ---- e2e: host buffer -> C ABI -> result, copies inside the timed region ----------------
+    e2e = None
+    if not args.no_e2e:
+        eg = args.e2e_gib or args.gib
+        n_host = min(int(eg * (1 << 30)), span)
+        try:
+            host = torch.empty(n_host, dtype=torch.uint8, pin_memory=True)
+        except Exception:
+            n_host = min(n_host, 1 << 30)
+            host = torch.empty(n_host, dtype=torch.uint8, pin_memory=True)
+        host.copy_(shard[:n_host])
+        torch.cuda.synchronize()
+        for _ in range(2):
+            assert searcher.find_in(host) is None
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r = searcher.find_in(host)  # ss_b200_find_in_host: chunked H2D + scan + result read
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert r is None
+        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dt = float(td[0])
+        chunk = int(os.environ.get("SS_B200_HOST_CHUNK_MIB", "64")) << 20
+        n_chunks = max(1, -(-(n_host - k + 1) // chunk))
+        e2e = {"value": round(n_host * world * args.e2e_steps / dt / 1e9, 3), "unit": UNIT,
+               "h2d_bytes_per_step": (n_host + (n_chunks - 1) * (k - 1)) * world,
+               "d2h_bytes_per_step": 8 * n_chunks * world,
+               "host_bytes_per_gpu": n_host, "steps": args.e2e_steps,
+               "timer": "host wall clock around the synchronous C-ABI call, max over ranks",
+               "call": "ss_b200_find_in_host (pinned host haystack, 64 MiB chunks, 3 staging buffers)"}
+        del host
+
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = extras_single_gpu(ss, torch, i386, shard, args)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        del shard
+        torch.cuda.empty_cache()
+        cpu = cpu_baseline(i386, needle, args.cpu_sample_gib)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / K, 5), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {
+                "workload": f"i386 long-haystack: data/i386.txt tiled to {args.gib:g} GiB per GPU, needle "
+                            f"{args.needle!r} (absent => full scan), DynamicAvx2Searcher::new semantics",
+                "haystack_bytes_per_gpu": S, "needle_len": k, "position": k - 1,
+                "sharding": "contiguous start-position ranges + k-1 byte right halo; NCCL all_reduce(MIN) of "
+                            "the 8-byte first offset per step" if world > 1 else "single GPU",
+                "l2": "haystack >> L2 (126 MB): every step streams from HBM, no flush needed",
+                "kernel_variant": {0: "auto", 1: "ldg", 2: "tma"}[args.variant],
+            },
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": UNIT,
+                         "frac": round(achieved / peak, 4), "peak_source": peak_src,
+                         "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                         "kernel_ms": round(kern_avg_ms, 5), "algorithmic_bytes_per_launch": kern_bytes,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "traffic_source": (traffic or {}).get("source")},
+            "cpu_baseline": cpu,
+            "parity": "needle absent on every step (result == DEVICE_NONE on all ranks); see tests/ -m gpu",
+        }
+        if extras:
+            line["extras"] = extras
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
