@@ -29,7 +29,7 @@ import numpy as np
 
 __all__ = ["DynamicB200Searcher", "B200Searcher", "DeviceHaystack", "SearcherPanic", "B200Error", "lib",
            "NPOS", "DEVICE_NONE", "fill_random", "fill_tiled", "set_scan_variant", "set_scan_tuning",
-           "launch_count", "Batch"]
+           "launch_count", "Batch", "set_extra_anchors"]
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsliceslice_b200.so")
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         "ss_b200_fill_tiled": (i32, [vp, sz, u64, vp, sz, vp]),
         "ss_b200_set_scan_variant": (i32, [i32]),
         "ss_b200_set_scan_tuning": (i32, [i32, i32, i32, i32]),
+        "ss_b200_set_extra_anchors": (i32, [i32]),
         "ss_b200_launch_count": (u64, []),
     }
     for name, (res, args) in sig.items():
@@ -355,6 +356,10 @@ def set_scan_variant(variant: int) -> None:
 
 def set_scan_tuning(ctas_per_sm: int = 0, unroll: int = 0, tile_kib: int = 0, stages: int = 0) -> None:
     _check(lib().ss_b200_set_scan_tuning(ctas_per_sm, unroll, tile_kib, stages))
+
+
+def set_extra_anchors(n: int = -1) -> None:
+    _check(lib().ss_b200_set_extra_anchors(n))
 
 
 def launch_count() -> int:

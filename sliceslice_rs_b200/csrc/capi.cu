@@ -99,6 +99,13 @@ extern "C" int ss_b200_set_scan_tuning(int ctas_per_sm, int unroll, int tile_kib
     g_tuning.stages = stages;
     return SS_B200_OK;
 }
+extern "C" int ss_b200_set_extra_anchors(int n)
+{
+    if (n < -1 || n > 3)
+        return SS_B200_E_ARG;
+    g_tuning.extra_anchors = n;
+    return SS_B200_OK;
+}
 extern "C" uint64_t ss_b200_launch_count(void) { return ss_host_launch_count(); }
 
 // ---------------------------------------------------------------------------------------------
@@ -316,9 +323,10 @@ static int build_args(const ss_b200_searcher *s, const void *dptr, size_t len, u
     const uint8_t f = s->needle[0], l = s->needle[s->position];
     a.f4 = 0x01010101u * f;
     a.l4 = 0x01010101u * l;
-    if (k <= SS_INLINE_NEEDLE_MAX) {
-        memcpy(a.needle_inline, s->needle.data(), k);
-    } else {
+    for (int e = 0; e < 3; e++) // extra word-aligned anchors: needle[4], needle[8], needle[12]
+        a.e4[e] = (4u * (e + 1) < k) ? 0x01010101u * s->needle[4 * (e + 1)] : 0u;
+    memcpy(a.needle_inline, s->needle.data(), k < SS_INLINE_NEEDLE_MAX ? k : SS_INLINE_NEEDLE_MAX);
+    if (k > SS_INLINE_NEEDLE_MAX) {
         int rc = needle_on_device(s, dev, &a.needle_g);
         if (rc != SS_B200_OK)
             return rc;

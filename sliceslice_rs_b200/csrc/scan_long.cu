@@ -1,52 +1,11 @@
-// scan_long.cu -- instantiation table and launcher for K1 (see scan_long.cuh).
+// scan_long.cu -- geometry and launcher for K1 (kernels: scan_long.cuh, tables: scan_tables.cuh).
 #include "scan_long.cuh"
 #include "ss_host.h"
 
 #include <atomic>
-#include <mutex>
 
 namespace {
-
-using LdgFn = void (*)(const ScanArgs);
-using TmaFn = void (*)(const ScanArgs, int, uint32_t);
-
-// index: [R][QZ]
-template <int U>
-struct LdgTable {
-    static LdgFn get(int r, bool qz)
-    {
-#define SS_ROW(R)                                                                                                    \
-    case R:                                                                                                          \
-        return qz ? (LdgFn)scan_ldg_kernel<R, true, false, U> : (LdgFn)scan_ldg_kernel<R, false, false, U>;
-        switch (r) {
-            SS_ROW(0) SS_ROW(1) SS_ROW(2) SS_ROW(3) SS_ROW(4) SS_ROW(5) SS_ROW(6) SS_ROW(7) SS_ROW(8) SS_ROW(9)
-            SS_ROW(10) SS_ROW(11) SS_ROW(12) SS_ROW(13) SS_ROW(14) SS_ROW(15)
-        }
-#undef SS_ROW
-        return nullptr;
-    }
-    static LdgFn k1() { return (LdgFn)scan_ldg_kernel<0, true, true, U>; }
-};
-
-template <int TILE>
-struct TmaTable {
-    static TmaFn get(int r, bool qz)
-    {
-#define SS_ROW(R)                                                                                                    \
-    case R:                                                                                                          \
-        return qz ? (TmaFn)scan_tma_kernel<R, true, false, TILE> : (TmaFn)scan_tma_kernel<R, false, false, TILE>;
-        switch (r) {
-            SS_ROW(0) SS_ROW(1) SS_ROW(2) SS_ROW(3) SS_ROW(4) SS_ROW(5) SS_ROW(6) SS_ROW(7) SS_ROW(8) SS_ROW(9)
-            SS_ROW(10) SS_ROW(11) SS_ROW(12) SS_ROW(13) SS_ROW(14) SS_ROW(15)
-        }
-#undef SS_ROW
-        return nullptr;
-    }
-    static TmaFn k1() { return (TmaFn)scan_tma_kernel<0, true, true, TILE>; }
-};
-
 std::atomic<uint64_t> g_launches{0};
-
 } // namespace
 
 uint64_t ss_host_launch_count() { return g_launches.load(std::memory_order_relaxed); }
@@ -64,15 +23,40 @@ void ss_host_scan_geometry(ScanArgs &a, unsigned long long start_limit)
     a.n_chunks = (a.head + end + 15) / 16;
     a.last_chunk = (a.head + a.n - 1) / 16;
     a.q = a.pos / 16;
+    a.bs = 8u * (a.pos % 4u);
 }
 
-cudaError_t ss_host_launch_scan(const ScanArgs &a, const SsScanTuning &t, const SsDeviceInfo &dev, cudaStream_t stream)
+// Number of word-aligned extra anchors (needle offsets 4, 8, 12) the filter can use for this needle.
+static int usable_extra_anchors(const ScanArgs &a)
 {
+    int ne = 0;
+    for (uint32_t off = 4; off <= 12 && off < a.k; off += 4)
+        ne++;
+    if (ne == 1 && a.pos == 4)
+        ne = 0; // the only extra anchor would repeat the second anchor
+    return ne;
+}
+
+cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, const SsDeviceInfo &dev,
+                                cudaStream_t stream)
+{
+    ScanArgs a = a_in;
     const bool k1 = (a.k == 1);
     const int r = k1 ? 0 : (int)(a.pos % 16);
+    const int ws = r / 4;
+    const bool bsz = (r % 4) == 0;
     const bool qz = k1 || a.pos < 16;
     const unsigned long long scan_bytes = a.n_chunks * 16ull;
-    const uint32_t halo = k1 ? 0u : 16u * (a.q + (r > 0 ? 1u : 0u));
+    // right halo of a staged tile: the next chunk (register window of the verify path and the
+    // extra anchors) and the second-anchor window at +q, +q+1
+    const uint32_t reach = k1 ? 0u : (a.q + (r > 0 ? 1u : 0u));
+    const uint32_t halo = k1 ? 0u : 16u * (reach > 1u ? reach : 1u);
+
+    int ne = usable_extra_anchors(a);
+    const int want = (t.extra_anchors >= 0) ? t.extra_anchors : 2;
+    if (ne > want)
+        ne = want;
+    a.ne = (uint32_t)ne;
 
     int variant = t.variant;
     if (variant == 0)
@@ -85,8 +69,7 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a, const SsScanTuning &t, const 
         const uint32_t tile = (uint32_t)tile_kib * 1024u;
         int stages = t.stages > 0 ? t.stages : 4;
         const uint32_t stage_stride = tile + ((halo + 127u) & ~127u);
-        TmaFn fn = (tile_kib == 32) ? (k1 ? TmaTable<32768>::k1() : TmaTable<32768>::get(r, qz))
-                                    : (k1 ? TmaTable<16384>::k1() : TmaTable<16384>::get(r, qz));
+        SsTmaFn fn = (tile_kib == 32) ? ss_table_tma_32(ws, bsz, qz, k1, ne) : ss_table_tma_16(ws, bsz, qz, k1, ne);
         size_t smem = (size_t)stages * stage_stride + (size_t)stages * 16 + (size_t)stages * 4 + 16;
         while (smem > (size_t)dev.max_smem_optin && stages > 2) {
             stages--;
@@ -109,22 +92,16 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a, const SsScanTuning &t, const 
             grid = n_tiles;
         if (grid < 1)
             grid = 1;
-        fn<<<(unsigned)grid, SS_TMA_THREADS, smem, stream>>>(a, stages, stage_stride);
+        fn<<<(unsigned)grid, SS_TMA_THREADS, smem, stream>>>(a, stages, stage_stride, halo);
         ss_host_count_launch(1);
         return cudaGetLastError();
     }
 
     // variant 1: direct LDG
     int u = t.unroll;
-    if (u != 1 && u != 2 && u != 4)
+    if (u != 1 && u != 4)
         u = (scan_bytes >= (4ull << 20)) ? 4 : 1;
-    LdgFn fn;
-    if (u == 4)
-        fn = k1 ? LdgTable<4>::k1() : LdgTable<4>::get(r, qz);
-    else if (u == 2)
-        fn = k1 ? LdgTable<2>::k1() : LdgTable<2>::get(r, qz);
-    else
-        fn = k1 ? LdgTable<1>::k1() : LdgTable<1>::get(r, qz);
+    SsLdgFn fn = (u == 4) ? ss_table_ldg_u4(ws, bsz, qz, k1, ne) : ss_table_ldg_u1(ws, bsz, qz, k1, ne);
     const unsigned long long cta_bytes = (unsigned long long)(SS_LDG_THREADS / 32) * u * 32 * 16;
     const unsigned long long n_tiles = (scan_bytes + cta_bytes - 1) / cta_bytes;
     int per_sm = t.ctas_per_sm > 0 ? t.ctas_per_sm : 6;

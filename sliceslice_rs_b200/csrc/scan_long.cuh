@@ -24,20 +24,24 @@
 #define SS_TMA_HALO_MAX 2048 // bytes of right halo a TMA stage can carry
 
 // ------------------------------------------------------------------------------------------
+// Template parameters shared by both variants (see ss_device.cuh filter_word):
+//   WS, BSZ  second-anchor byte shift R = pos % 16 split as word offset WS = R / 4 (static) and bit
+//            shift bs = 8 * (R % 4) (launch-uniform runtime value; BSZ <=> bs == 0, no funnel shift)
+//   QZ       pos / 16 == 0: the second-anchor window is the lane's own chunk + the next one
+//   K1       one-byte needle (memchr path of src/lib.rs:130-136): first anchor only
+//   NE       extra word-aligned anchors (needle offsets 4, 8, 12) folded into the filter
+//
 // Variant 1: direct LDG.  CTA tile = WARPS * U * 32 chunks; warp w owns a contiguous run of
 // U*32 chunks of it; tiles are dealt blocked-cyclically so the grid sweeps the haystack as a
 // moving band (good for early exit and DRAM page locality).
-//   R   = pos % 16   (compile time: byte shift of the second anchor stream)
-//   QZ  = pos / 16 == 0  (the B window starts in the lane's own chunk)
-//   K1  = one-byte needle (memchr path of src/lib.rs:130-136): first anchor only
 //   U   = chunks per lane per step (independent 16-byte loads in flight)
 // One warp step: U*32 chunks starting at chunk `cw` (lane l takes cw + l + 32u).
 // CLAMP=false is the interior fast path (every load provably in range: plain base+immediate
 // addressing); CLAMP=true clamps each chunk index to the last loadable chunk (tail tiles).
 // Returns true when the early-exit test says this CTA can stop.
-template <int R, bool QZ, bool K1, int U, bool CLAMP>
+template <int WS, bool BSZ, bool QZ, bool K1, int NE, int U, bool CLAMP>
 __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restrict__ chunks, unsigned long long cw,
-                                         int lane, uint32_t f4, uint32_t l4)
+                                         int lane, uint32_t f4, uint32_t l4, uint32_t bs, const uint32_t (&e4)[3])
 {
     // early exit: nothing at or right of this warp's first position can beat the current best
     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
@@ -45,27 +49,33 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
     const unsigned long long c0 = cw + lane;
     const uint4 *p = chunks + c0;
     const uint4 *pq = p + a.q;
+    constexpr bool NEED_HI = !(BSZ && WS == 0); // second-anchor window spills into the following chunk
 
-    uint4 av[U], lo[U], hi[U];
+    uint4 av[U], nx[U], lo[U], hi[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         if (CLAMP) {
             const unsigned long long c = c0 + u * 32;
             av[u] = ldg16(chunks + (c < last ? c : last));
+            nx[u] = K1 ? av[u] : ldg16(chunks + (c + 1 < last ? c + 1 : last));
         } else {
             av[u] = ldg16(p + u * 32);
+            nx[u] = K1 ? av[u] : ldg16(p + u * 32 + 1);
         }
     }
     if (!K1) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (CLAMP) {
+            if (QZ) {
+                lo[u] = av[u];
+                hi[u] = nx[u];
+            } else if (CLAMP) {
                 const unsigned long long c = c0 + u * 32 + a.q;
-                lo[u] = QZ ? av[u] : ldg16(chunks + (c < last ? c : last));
-                hi[u] = (R > 0) ? ldg16(chunks + (c + 1 < last ? c + 1 : last)) : lo[u];
+                lo[u] = ldg16(chunks + (c < last ? c : last));
+                hi[u] = NEED_HI ? ldg16(chunks + (c + 1 < last ? c + 1 : last)) : lo[u];
             } else {
-                lo[u] = QZ ? av[u] : ldg16(pq + u * 32);
-                hi[u] = (R > 0) ? ldg16(pq + u * 32 + 1) : lo[u];
+                lo[u] = ldg16(pq + u * 32);
+                hi[u] = NEED_HI ? ldg16(pq + u * 32 + 1) : lo[u];
             }
         }
     }
@@ -78,7 +88,7 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
     uint32_t any = 0;
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        fl[u] = chunk_flag<R, K1>(av[u], lo[u], hi[u], f4, l4);
+        fl[u] = chunk_flag_x<WS, BSZ, K1, NE>(av[u], nx[u], lo[u], hi[u], f4, l4, bs, e4);
         any |= fl[u];
     }
     if (__any_sync(0xFFFFFFFFu, any != 0)) {
@@ -86,13 +96,13 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
         for (int u = 0; u < U; u++) {
             const unsigned long long c = c0 + u * 32;
             if (fl[u] && (!CLAMP || c < a.n_chunks))
-                verify_chunk<R, K1>(a, av[u], lo[u], hi[u], c);
+                verify_chunk<WS, BSZ, K1, NE>(a, av[u], nx[u], lo[u], hi[u], c);
         }
     }
     return false;
 }
 
-template <int R, bool QZ, bool K1, int U>
+template <int WS, bool BSZ, bool QZ, bool K1, int NE, int U>
 __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_constant__ ScanArgs a)
 {
     constexpr int WARPS = SS_LDG_THREADS / 32;
@@ -101,25 +111,27 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned long long n_tiles = (a.n_chunks + CTA_CHUNKS - 1) / CTA_CHUNKS;
-    // tiles [0, n_interior): every chunk holds start positions and every load (incl. the
-    // second-anchor window at +q, +q+1) stays at or below last_chunk
+    // tiles [0, n_interior): every chunk holds start positions and every load (incl. the next chunk
+    // and the second-anchor window at +q, +q+1) stays at or below last_chunk
     unsigned long long n_interior = a.n_chunks / CTA_CHUNKS;
     {
-        const unsigned long long lim = (a.last_chunk >= a.q) ? (a.last_chunk - a.q) / CTA_CHUNKS : 0;
+        const unsigned long long reach = a.q + 1;
+        const unsigned long long lim = (a.last_chunk >= reach) ? (a.last_chunk - reach + 1) / CTA_CHUNKS : 0;
         if (lim < n_interior)
             n_interior = lim;
     }
-    const uint32_t f4 = a.f4, l4 = a.l4;
+    const uint32_t f4 = a.f4, l4 = a.l4, bs = a.bs;
+    const uint32_t e4[3] = {a.e4[0], a.e4[1], a.e4[2]};
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
         bool stop;
         if (tile < n_interior) {
-            stop = ldg_step<R, QZ, K1, U, false>(a, chunks, cw, lane, f4, l4);
+            stop = ldg_step<WS, BSZ, QZ, K1, NE, U, false>(a, chunks, cw, lane, f4, l4, bs, e4);
         } else {
             if (cw >= a.n_chunks)
                 continue; // this warp's run holds no start position (warp-uniform)
-            stop = ldg_step<R, QZ, K1, U, true>(a, chunks, cw, lane, f4, l4);
+            stop = ldg_step<WS, BSZ, QZ, K1, NE, U, true>(a, chunks, cw, lane, f4, l4, bs, e4);
         }
         if (stop)
             break; // every later tile of this CTA is further right still
@@ -129,20 +141,21 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
 
 // ------------------------------------------------------------------------------------------
 // Variant 2: TMA-staged.  One producer warp (one elected lane) streams tiles of TILE bytes plus
-// a right halo of 16*(q + (R>0)) bytes into a ring of `stages` shared-memory buffers with
+// a right halo of 16*max(q + (R>0), 1) bytes into a ring of `stages` shared-memory buffers with
 // cp.async.bulk; SS_TMA_CONSUMER_WARPS warps wait on the stage's "full" mbarrier, run the same
 // SWAR filter out of shared memory, and release the stage through its "empty" mbarrier.
 // Dynamic smem layout: [stages][stage_stride] data, then full[stages], empty[stages] mbarriers,
 // then one uint32 "valid" word per stage (0 = producer stopped: early exit or end of work).
-template <int R, bool QZ, bool K1, int TILE>
-__global__ void __launch_bounds__(SS_TMA_THREADS) scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages,
-                                                                  uint32_t stage_stride)
+template <int WS, bool BSZ, bool QZ, bool K1, int NE, int TILE>
+__global__ void __launch_bounds__(SS_TMA_THREADS, 3) scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages,
+                                                                  uint32_t stage_stride, uint32_t halo)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int CW = SS_TMA_CONSUMER_WARPS;
     constexpr int TILE_CHUNKS = TILE / 16;
     constexpr int WARP_CHUNKS = TILE_CHUNKS / CW; // contiguous run per consumer warp
     constexpr int U = 4;
+    constexpr bool NEED_HI = !(BSZ && WS == 0);
     static_assert(WARP_CHUNKS % (32 * U) == 0, "tile must split into whole 32*U-chunk steps per warp");
 
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)stages * stage_stride);
@@ -152,7 +165,6 @@ __global__ void __launch_bounds__(SS_TMA_THREADS) scan_tma_kernel(const __grid_c
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned long long n_tiles = (a.n_chunks + TILE_CHUNKS - 1) / TILE_CHUNKS;
-    const uint32_t halo = K1 ? 0u : 16u * (a.q + (R > 0 ? 1u : 0u));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; s++) {
@@ -201,7 +213,8 @@ __global__ void __launch_bounds__(SS_TMA_THREADS) scan_tma_kernel(const __grid_c
         }
     } else {
         // ===== consumers =====
-        const uint32_t f4 = a.f4, l4 = a.l4;
+        const uint32_t f4 = a.f4, l4 = a.l4, bs = a.bs;
+        const uint32_t e4[3] = {a.e4[0], a.e4[1], a.e4[2]};
         const uint32_t qb = a.q * 16u;
         int s = 0;
         uint32_t ph = 0;
@@ -214,23 +227,30 @@ __global__ void __launch_bounds__(SS_TMA_THREADS) scan_tma_kernel(const __grid_c
 #pragma unroll 1
             for (int step = 0; step < WARP_CHUNKS / (32 * U); step++) {
                 const uint32_t lc0 = (uint32_t)warp * WARP_CHUNKS + step * (32 * U) + lane; // chunk within tile
-                uint4 av[U], lo[U], hi[U];
+                uint4 av[U], nx[U], lo[U], hi[U];
 #pragma unroll
-                for (int u = 0; u < U; u++)
+                for (int u = 0; u < U; u++) {
                     av[u] = lds16(st + (lc0 + u * 32) * 16u);
+                    nx[u] = K1 ? av[u] : lds16(st + (lc0 + u * 32) * 16u + 16u);
+                }
                 if (!K1) {
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const uint32_t b = (lc0 + u * 32) * 16u + qb;
-                        lo[u] = QZ ? av[u] : lds16(st + b);
-                        hi[u] = (R > 0) ? lds16(st + b + 16u) : lo[u];
+                        if (QZ) {
+                            lo[u] = av[u];
+                            hi[u] = nx[u];
+                        } else {
+                            const uint32_t b = (lc0 + u * 32) * 16u + qb;
+                            lo[u] = lds16(st + b);
+                            hi[u] = NEED_HI ? lds16(st + b + 16u) : lo[u];
+                        }
                     }
                 }
                 uint32_t fl[U];
                 uint32_t any = 0;
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    fl[u] = chunk_flag<R, K1>(av[u], lo[u], hi[u], f4, l4);
+                    fl[u] = chunk_flag_x<WS, BSZ, K1, NE>(av[u], nx[u], lo[u], hi[u], f4, l4, bs, e4);
                     any |= fl[u];
                 }
                 if (__any_sync(0xFFFFFFFFu, any != 0)) {
@@ -238,7 +258,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS) scan_tma_kernel(const __grid_c
                     for (int u = 0; u < U; u++) {
                         const unsigned long long c = tile_c0 + lc0 + u * 32;
                         if (fl[u] && c < a.n_chunks)
-                            verify_chunk<R, K1>(a, av[u], lo[u], hi[u], c);
+                            verify_chunk<WS, BSZ, K1, NE>(a, av[u], nx[u], lo[u], hi[u], c);
                     }
                 }
             }

@@ -43,7 +43,10 @@ struct ScanArgs {
     uint32_t head; // hay - align_down(hay, 16), 0..15
     uint32_t f4;   // needle[0] splatted x4
     uint32_t l4;   // needle[pos] splatted x4
-    uint8_t needle_inline[SS_INLINE_NEEDLE_MAX];
+    uint32_t bs;   // 8 * (pos % 4): bit shift of the second-anchor stream inside a word
+    uint32_t ne;   // extra word-aligned anchors in use (needle offsets 4, 8, 12), 0..3
+    uint32_t e4[3]; // needle[4], needle[8], needle[12] splatted x4
+    uint8_t needle_inline[SS_INLINE_NEEDLE_MAX]; // first min(k, 64) needle bytes
 };
 
 __device__ __forceinline__ uint4 ldg16(const uint4 *p)
@@ -91,10 +94,54 @@ __device__ __forceinline__ uint32_t window_word(const uint4 &lo, const uint4 &hi
     return __funnelshift_r(v[ws + j], v[ws + j + 1], bs);
 }
 
-// Candidate test for the 16 start positions of one chunk.
-//   a  : haystack bytes [16c, 16c+16)
-//   lo : haystack bytes [16(c+q), +16), hi: the next 16 (only read when R > 0)
-// Returns non-zero iff some position MAY satisfy hay[i]==first && hay[i+pos]==last.
+// Same with the shift split as R = 4*WS + bs/8: the word offset WS is a template parameter (register
+// selection must be static), the bit shift `bs` (8, 16 or 24) is a launch-uniform runtime value, and
+// BSZ says bs == 0 (no funnel shift at all).  8 instantiations cover the 16 byte shifts.
+template <int WS, bool BSZ>
+__device__ __forceinline__ uint32_t window_word_rt(const uint4 &lo, const uint4 &hi, int j, uint32_t bs)
+{
+    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (BSZ)
+        return v[WS + j];
+    return __funnelshift_r(v[WS + j], v[WS + j + 1], bs);
+}
+
+// The filter word for 4 start positions (word j of a chunk):
+//   zero byte <=> hay[i] == needle[0] && hay[i+pos] == needle[pos] && hay[i+4e] == needle[4e] (e = 1..NE)
+// The first two terms are the reference's two anchors (VectorHash first/last, src/lib.rs:166-178,
+// :207-214).  The NE extra anchors sit at needle offsets 4, 8, 12: those byte streams are word-aligned
+// with the first one, so each costs one LOP3 per word and no shift.  They only make the filter more
+// selective (fewer trips to the divergent verify path on natural text); a real match always passes.
+//   av : haystack bytes [16c, 16c+16)      nx : the next 16 bytes [16c+16, 16c+32)
+//   lo : haystack bytes [16(c+q), +16)     hi : the 16 after lo (lo/hi == av/nx when q == 0)
+template <int WS, bool BSZ, bool K1, int NE>
+__device__ __forceinline__ uint32_t filter_word(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi,
+                                                int j, uint32_t f4, uint32_t l4, uint32_t bs, const uint32_t (&e4)[3])
+{
+    const uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
+    uint32_t x = w[j] ^ f4;
+    if (!K1) {
+        x |= window_word_rt<WS, BSZ>(lo, hi, j, bs) ^ l4;
+#pragma unroll
+        for (int e = 0; e < NE; e++)
+            x |= w[j + e + 1] ^ e4[e];
+    }
+    return x;
+}
+
+// Candidate test for the 16 start positions of one chunk: non-zero iff some position MAY pass the filter.
+template <int WS, bool BSZ, bool K1, int NE>
+__device__ __forceinline__ uint32_t chunk_flag_x(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi,
+                                                 uint32_t f4, uint32_t l4, uint32_t bs, const uint32_t (&e4)[3])
+{
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        acc |= swar_zero_term(filter_word<WS, BSZ, K1, NE>(av, nx, lo, hi, j, f4, l4, bs, e4));
+    return acc & 0x80808080u;
+}
+
+// Two-anchor form with a compile-time byte shift (used by the batched multi-needle kernel).
 template <int R, bool K1>
 __device__ __forceinline__ uint32_t chunk_flag(const uint4 &a, const uint4 &lo, const uint4 &hi, uint32_t f4,
                                                uint32_t l4)
@@ -111,19 +158,19 @@ __device__ __forceinline__ uint32_t chunk_flag(const uint4 &a, const uint4 &lo, 
     return acc & 0x80808080u;
 }
 
-// memcmp of needle[1..k) against h[1..k) -- the verify of src/lib.rs:216-244
-// (byte 0 is already proven equal by the filter).
-__device__ __forceinline__ bool needle_tail_equal(const ScanArgs &a, const uint8_t *h)
+// memcmp of needle[from..k) against h[from..k) from global memory -- only reached by needles longer
+// than the 17 bytes the register window covers, after those 17 bytes already matched.
+static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const uint8_t *h, uint32_t from)
 {
     const uint32_t k = a.k;
     if (k <= SS_INLINE_NEEDLE_MAX) {
-        for (uint32_t j = 1; j < k; j++)
+        for (uint32_t j = from; j < k; j++)
             if (__ldg(h + j) != a.needle_inline[j])
                 return false;
         return true;
     }
     const uint8_t *nd = a.needle_g;
-    uint32_t j = 1;
+    uint32_t j = from;
     // byte steps until h + j is 8-byte aligned, then 8 bytes of haystack per step
     for (; j < k && ((reinterpret_cast<uintptr_t>(h + j)) & 7); j++)
         if (__ldg(h + j) != __ldg(nd + j))
@@ -143,26 +190,51 @@ __device__ __forceinline__ bool needle_tail_equal(const ScanArgs &a, const uint8
     return true;
 }
 
-// Hit path for one chunk whose SWAR flag fired: exact per-byte decode in ascending
-// position order (the ctz loop of src/lib.rs:220-248), range check, verify, publish.
-template <int R, bool K1>
-__device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 lo, uint4 hi, unsigned long long chunk)
+// Hit path for one chunk whose SWAR flag fired -- the ctz loop + memcmp of src/lib.rs:216-248, done
+// without touching memory: the lane already holds the 32 haystack bytes [16c, 16c+32) in registers,
+// which cover needle bytes 0..16 of every start position of the chunk.  `z` keeps one bit per still-
+// alive start position; each round slides the window by one byte and ANDs in the exact compare with
+// the next needle byte for all 16 positions at once.  Natural-text false candidates die in the first
+// round or two.  Survivors (17 bytes equal) of longer needles finish from global memory.
+template <int WS, bool BSZ, bool K1, int NE>
+__device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx, uint4 lo, uint4 hi,
+                                          unsigned long long chunk)
 {
-    const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+    uint32_t e4[3] = {a.e4[0], a.e4[1], a.e4[2]};
+    uint32_t z[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, NE>(av, nx, lo, hi, j, a.f4, a.l4, a.bs, e4));
+    if (!K1) {
+        uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
+        const uint32_t jmax = a.k - 1 < 16u ? a.k - 1 : 16u;
+        for (uint32_t j = 1; j <= jmax; j++) {
+#pragma unroll
+            for (int t = 0; t < 7; t++)
+                w[t] = __funnelshift_r(w[t], w[t + 1], 8);
+            w[7] >>= 8;
+            const uint32_t n4 = 0x01010101u * a.needle_inline[j];
+            uint32_t any = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                z[t] &= swar_zero_exact(w[t] ^ n4);
+                any |= z[t];
+            }
+            if (!any)
+                return;
+        }
+    }
     const long long p0 = (long long)(chunk * 16ull) - (long long)a.head; // position of byte 0 of the chunk
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        uint32_t x = aw[j] ^ a.f4;
-        if (!K1)
-            x |= window_word<R>(lo, hi, j) ^ a.l4;
-        uint32_t z = swar_zero_exact(x);
-        while (z) {
-            const int bit = __ffs((int)z) - 1;
-            z &= z - 1;
+        uint32_t zz = z[j];
+        while (zz) {
+            const int bit = __ffs((int)zz) - 1;
+            zz &= zz - 1;
             const long long i = p0 + 4 * j + (bit >> 3);
             if (i < 0 || (unsigned long long)i >= a.end)
                 continue;
-            if (K1 || needle_tail_equal(a, a.hay + i)) {
+            if (K1 || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
                 atomicMax(&a.ws->key, ~(unsigned long long)i);
                 __threadfence();
                 return; // ascending order: later positions of this chunk cannot be smaller

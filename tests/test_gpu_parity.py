@@ -237,6 +237,35 @@ def test_randomized_differential(alphabet, variant):
         s.close()
 
 
+@pytest.mark.parametrize("ne", [0, 1, 2, 3])
+def test_extra_anchor_settings_do_not_change_results(ne, variant):
+    # the word-aligned extra anchors (needle offsets 4, 8, 12) only thin out the candidates
+    ss.set_extra_anchors(ne)
+    try:
+        rng = random.Random(500 + ne)
+        pool = torch.empty(70000, dtype=torch.uint8, device="cuda")
+        for it in range(600):
+            alphabet = rng.choice([2, 3, 4])
+            n = rng.randrange(0, 600) if it % 4 else rng.randrange(30000, 66000)
+            k = rng.randrange(1, 48)
+            h = bytes(rng.randrange(alphabet) + 97 for _ in range(n))
+            if n >= k and rng.random() < 0.5:
+                st = rng.randrange(0, n - k + 1)
+                nd = h[st:st + k]
+            else:
+                nd = bytes(rng.randrange(alphabet) + 97 for _ in range(k))
+            pos = 0 if k <= 1 else rng.randrange(k)
+            a = rng.randrange(32)
+            if n:
+                pool[a:a + n] = torch.frombuffer(bytearray(h), dtype=torch.uint8).cuda()
+            pool[a + n:a + n + 64] = nd[0]
+            s = ss.DynamicB200Searcher.with_position(nd, pos)
+            assert s.find_in(pool[a:a + n]) == oracle.find(h, nd, pos) == _expect(h, nd), (h[:80], nd, pos, a)
+            s.close()
+    finally:
+        ss.set_extra_anchors(-1)
+
+
 def test_adversarial_all_candidates(variant):
     # every position passes the filter (src/x86.rs:252-255 motivates `position`)
     n = 1 << 20

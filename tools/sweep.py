@@ -46,8 +46,8 @@ def main():
         needles = [x.encode("latin-1") for x in (a.needles.split(",") if a.needles else TEXT_NEEDLES)]
     ws = torch.zeros(16, dtype=torch.uint8, device="cuda")
     res = torch.zeros(1, dtype=torch.int64, device="cuda")
-    print(f"haystack {a.gib} GiB {'random' if a.random else 'i386-tiled'}; GB/s per (variant:ctas,unroll,tile_kib,stages)")
-    hdr = "needle".ljust(34) + "".join(g.rjust(16) for g in a.grid.split())
+    print(f"haystack {a.gib} GiB {'random' if a.random else 'i386-tiled'}; GB/s per (variant:ctas,unroll,tile_kib,stages[,extra_anchors])")
+    hdr = "needle".ljust(34) + "".join(g.rjust(18) for g in a.grid.split())
     print(hdr)
     for nd in needles:
         row = (repr(nd)[:30] + f" k={len(nd)}").ljust(34)
@@ -55,7 +55,9 @@ def main():
         for g in a.grid.split():
             v, t = g.split(":")
             ss.set_scan_variant(int(v))
-            ss.set_scan_tuning(*[int(x) for x in t.split(",")])
+            tt = [int(x) for x in t.split(",")]
+            ss.set_scan_tuning(*tt[:4])
+            ss.set_extra_anchors(tt[4] if len(tt) > 4 else -1)
             for _ in range(2):
                 s.find_in_async(hay, res, ws)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -65,7 +67,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             assert int(res.item()) == ss.DEVICE_NONE
-            row += f"{n * a.reps / (e0.elapsed_time(e1) * 1e-3) / 1e9:16.1f}"
+            row += f"{n * a.reps / (e0.elapsed_time(e1) * 1e-3) / 1e9:18.1f}"
         print(row, flush=True)
 
 
