@@ -65,9 +65,9 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
         variant = 1; // second anchor too far away for a staged tile; LDG path handles any distance
 
     if (variant == 2) {
-        const int tile_kib = (t.tile_kib == 32) ? 32 : 16;
+        const int tile_kib = (t.tile_kib == 16) ? 16 : 32;
         const uint32_t tile = (uint32_t)tile_kib * 1024u;
-        int stages = t.stages > 0 ? t.stages : 4;
+        int stages = t.stages > 0 ? t.stages : 3;
         const uint32_t stage_stride = tile + ((halo + 127u) & ~127u);
         SsTmaFn fn = (tile_kib == 32) ? ss_table_tma_32(ws, bsz, qz, k1, ne) : ss_table_tma_16(ws, bsz, qz, k1, ne);
         size_t smem = (size_t)stages * stage_stride + (size_t)stages * 16 + (size_t)stages * 4 + 16;

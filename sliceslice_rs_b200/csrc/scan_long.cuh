@@ -147,14 +147,14 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
 // Dynamic smem layout: [stages][stage_stride] data, then full[stages], empty[stages] mbarriers,
 // then one uint32 "valid" word per stage (0 = producer stopped: early exit or end of work).
 template <int WS, bool BSZ, bool QZ, bool K1, int NE, int TILE>
-__global__ void __launch_bounds__(SS_TMA_THREADS, 3) scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages,
+__global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3)) scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages,
                                                                   uint32_t stage_stride, uint32_t halo)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int CW = SS_TMA_CONSUMER_WARPS;
     constexpr int TILE_CHUNKS = TILE / 16;
     constexpr int WARP_CHUNKS = TILE_CHUNKS / CW; // contiguous run per consumer warp
-    constexpr int U = 4;
+    constexpr int U = QZ ? 4 : 2; // four live 16-byte vectors per chunk when the second anchor is >= 16 away
     constexpr bool NEED_HI = !(BSZ && WS == 0);
     static_assert(WARP_CHUNKS % (32 * U) == 0, "tile must split into whole 32*U-chunk steps per warp");
 
