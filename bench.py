@@ -186,7 +186,21 @@ def cpu_baseline(i386: bytes, needle: bytes, sample_gib: float):
         r = oracle.find(hay, needle, threads=cores)
         mt.append(time.perf_counter() - t0)
         assert r is None
+    # the literal configs 2 and 3 on one host thread, for the `extras` block of the GPU arm
+    with open(os.path.join(ROOT, "data", "words.txt"), "rb") as f:
+        words = [w for w in f.read().split(b"\n") if w]
+    sw = [words[i] for i in sorted(range(len(words)), key=lambda i: (len(words[i]), i))]
+    c2, c3 = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        offs = oracle.long_sweep(words, i386)
+        c2.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        m, _bm = oracle.short_sweep(sw, want_bitmap=False)
+        c3.append(time.perf_counter() - t0)
+    assert int(offs.sum()) == 809985317 and m == 39105
     return {"value": round(one, 3), "unit": UNIT, "cores": 1, "kind": "port",
+            "config2_literal_ms": round(min(c2) * 1e3, 3), "config3_short_ms": round(min(c3) * 1e3, 3),
             "sample": f"i386.txt tiled to {sample_gib:g} GiB in host DRAM, needle {needle!r} absent, "
                       f"{len(times)} full scans, median; C restatement of DynamicAvx2Searcher (gcc -O3 -mavx2)",
             "all_cores": {"value": round(n / min(mt) / 1e9, 3), "cores": cores}}
@@ -279,6 +293,22 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         "examined_bytes": 810016020, "sum_first_offsets": 809985317,
         "readme_i7_6700_ms": 35.181,
         "note": "L2-resident and early-exit: launch-latency-bound, no HBM-fraction claim",
+    }
+    sw = [words[i] for i in sorted(range(len(words)), key=lambda i: (len(words[i]), i))]
+    tri = ss.Batch(sw, sw)
+    tbest = None
+    for it in range(4):
+        t0 = time.perf_counter()
+        bm, matches = tri.search_triangular()
+        dt = time.perf_counter() - t0
+        if it:
+            tbest = dt if tbest is None else min(tbest, dt)
+    assert matches == 39105
+    out["config3_short_haystack"] = {
+        "what": "every word in every not-shorter word (10513405 pairs, bench/benches/i386.rs:118-131), one "
+                "batched launch, bitmap copied back to the host, host wall clock",
+        "ms_per_iteration": round(tbest * 1e3, 3), "ns_per_pair": round(tbest * 1e9 / 10513405, 4),
+        "matches": int(matches), "readme_i7_6700_ms": 79.416,
     }
     return out
 

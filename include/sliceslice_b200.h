@@ -182,8 +182,9 @@ int ss_b200_fill_tiled(void *d_dst, size_t len, uint64_t global_start, const voi
 int ss_b200_set_scan_variant(int variant);
 /* Overrides: ctas_per_sm (0 = auto), ... see DESIGN.md. */
 int ss_b200_set_scan_tuning(int ctas_per_sm, int unroll, int tile_kib, int stages);
-/* Word-aligned extra anchors (needle offsets 4, 8, 12) folded into the two-anchor filter of the
- * long scan: 0..3, or -1 = auto.  Changes the candidate rate only, never a result. */
+/* Extra anchors the long scan may fold into the two-anchor filter when it sees many candidates
+ * (word-aligned needle offsets 4 and 8, or one of 1..3 for short needles): 0 = never, 1 or -1 =
+ * adaptive per warp (default).  Changes the candidate rate only, never a result. */
 int ss_b200_set_extra_anchors(int n);
 /* Number of kernel launches issued by this library in this process so far. */
 uint64_t ss_b200_launch_count(void);

@@ -101,7 +101,7 @@ extern "C" int ss_b200_set_scan_tuning(int ctas_per_sm, int unroll, int tile_kib
 }
 extern "C" int ss_b200_set_extra_anchors(int n)
 {
-    if (n < -1 || n > 3)
+    if (n < -1 || n > 1)
         return SS_B200_E_ARG;
     g_tuning.extra_anchors = n;
     return SS_B200_OK;
@@ -323,8 +323,6 @@ static int build_args(const ss_b200_searcher *s, const void *dptr, size_t len, u
     const uint8_t f = s->needle[0], l = s->needle[s->position];
     a.f4 = 0x01010101u * f;
     a.l4 = 0x01010101u * l;
-    for (int e = 0; e < 3; e++) // extra word-aligned anchors: needle[4], needle[8], needle[12]
-        a.e4[e] = (4u * (e + 1) < k) ? 0x01010101u * s->needle[4 * (e + 1)] : 0u;
     memcpy(a.needle_inline, s->needle.data(), k < SS_INLINE_NEEDLE_MAX ? k : SS_INLINE_NEEDLE_MAX);
     if (k > SS_INLINE_NEEDLE_MAX) {
         int rc = needle_on_device(s, dev, &a.needle_g);

@@ -26,15 +26,38 @@ void ss_host_scan_geometry(ScanArgs &a, unsigned long long start_limit)
     a.bs = 8u * (a.pos % 4u);
 }
 
-// Number of word-aligned extra anchors (needle offsets 4, 8, 12) the filter can use for this needle.
-static int usable_extra_anchors(const ScanArgs &a)
+// Choose the extra anchors the filter may switch on (filter_word in ss_device.cuh): word-aligned
+// needle offsets 4 and 8 when the needle has them, else one unaligned offset for short needles.
+// Offsets equal to 0 or `pos` would repeat an anchor and are skipped.  Needs the first bytes of the
+// needle in a.needle_inline.
+static void choose_extra_anchors(ScanArgs &a, int allow)
 {
-    int ne = 0;
-    for (uint32_t off = 4; off <= 12 && off < a.k; off += 4)
-        ne++;
-    if (ne == 1 && a.pos == 4)
-        ne = 0; // the only extra anchor would repeat the second anchor
-    return ne;
+    a.xk = 0;
+    a.e4[0] = a.e4[1] = 0;
+    a.xbs = 0;
+    if (allow == 0 || a.k < 3)
+        return; // k == 2: the two anchors already are the whole needle
+    const bool has4 = a.k > 4 && a.pos != 4;
+    const bool has8 = a.k > 8 && a.pos != 8;
+    if (has4 && has8) {
+        a.xk = 2;
+        a.e4[0] = 0x01010101u * a.needle_inline[4];
+        a.e4[1] = 0x01010101u * a.needle_inline[8];
+    } else if (has4) {
+        a.xk = 1;
+        a.e4[0] = 0x01010101u * a.needle_inline[4];
+    } else {
+        // unaligned: the needle offset in 1..3 furthest from both anchors
+        uint32_t best = 0;
+        for (uint32_t o = 1; o <= 3 && o < a.k; o++)
+            if (o != a.pos && (best == 0 || o == 2))
+                best = o;
+        if (best) {
+            a.xk = 3;
+            a.e4[0] = 0x01010101u * a.needle_inline[best];
+            a.xbs = 8u * best;
+        }
+    }
 }
 
 cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, const SsDeviceInfo &dev,
@@ -52,11 +75,8 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
     const uint32_t reach = k1 ? 0u : (a.q + (r > 0 ? 1u : 0u));
     const uint32_t halo = k1 ? 0u : 16u * (reach > 1u ? reach : 1u);
 
-    int ne = usable_extra_anchors(a);
-    const int want = (t.extra_anchors >= 0) ? t.extra_anchors : 2;
-    if (ne > want)
-        ne = want;
-    a.ne = (uint32_t)ne;
+    choose_extra_anchors(a, t.extra_anchors);
+    const int xk = (int)a.xk;
 
     int variant = t.variant;
     if (variant == 0)
@@ -69,7 +89,7 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
         const uint32_t tile = (uint32_t)tile_kib * 1024u;
         int stages = t.stages > 0 ? t.stages : 3;
         const uint32_t stage_stride = tile + ((halo + 127u) & ~127u);
-        SsTmaFn fn = (tile_kib == 32) ? ss_table_tma_32(ws, bsz, qz, k1, ne) : ss_table_tma_16(ws, bsz, qz, k1, ne);
+        SsTmaFn fn = (tile_kib == 32) ? ss_table_tma_32(ws, bsz, qz, k1, xk) : ss_table_tma_16(ws, bsz, qz, k1, xk);
         size_t smem = (size_t)stages * stage_stride + (size_t)stages * 16 + (size_t)stages * 4 + 16;
         while (smem > (size_t)dev.max_smem_optin && stages > 2) {
             stages--;
@@ -101,7 +121,7 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
     int u = t.unroll;
     if (u != 1 && u != 4)
         u = (scan_bytes >= (4ull << 20)) ? 4 : 1;
-    SsLdgFn fn = (u == 4) ? ss_table_ldg_u4(ws, bsz, qz, k1, ne) : ss_table_ldg_u1(ws, bsz, qz, k1, ne);
+    SsLdgFn fn = (u == 4) ? ss_table_ldg_u4(ws, bsz, qz, k1, xk) : ss_table_ldg_u1(ws, bsz, qz, k1, xk);
     const unsigned long long cta_bytes = (unsigned long long)(SS_LDG_THREADS / 32) * u * 32 * 16;
     const unsigned long long n_tiles = (scan_bytes + cta_bytes - 1) / cta_bytes;
     int per_sm = t.ctas_per_sm > 0 ? t.ctas_per_sm : 6;

@@ -29,8 +29,45 @@
 //            shift bs = 8 * (R % 4) (launch-uniform runtime value; BSZ <=> bs == 0, no funnel shift)
 //   QZ       pos / 16 == 0: the second-anchor window is the lane's own chunk + the next one
 //   K1       one-byte needle (memchr path of src/lib.rs:130-136): first anchor only
-//   NE       extra word-aligned anchors (needle offsets 4, 8, 12) folded into the filter
-//
+//   XK       kind of extra anchors this needle offers (0 none); each warp switches them on and off
+//            with the verify-path trip rate it observes (AdaptiveFilter)
+
+// Filter flags for the U chunks of one warp step; returns the OR of the flags.
+template <int WS, bool BSZ, bool K1, int XK, int U>
+__device__ __forceinline__ uint32_t step_flags(const uint4 (&av)[U], const uint4 (&nx)[U], const uint4 (&lo)[U],
+                                               const uint4 (&hi)[U], const FilterConsts &fc, bool extras,
+                                               uint32_t (&fl)[U])
+{
+    uint32_t any = 0;
+    if (XK != 0 && extras) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            fl[u] = chunk_flag_x<WS, BSZ, K1, XK>(av[u], nx[u], lo[u], hi[u], fc);
+            any |= fl[u];
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            fl[u] = chunk_flag_x<WS, BSZ, K1, 0>(av[u], nx[u], lo[u], hi[u], fc);
+            any |= fl[u];
+        }
+    }
+    return any;
+}
+
+__device__ __forceinline__ FilterConsts load_filter_consts(const ScanArgs &a)
+{
+    FilterConsts fc;
+    fc.f4 = a.f4;
+    fc.l4 = a.l4;
+    fc.bs = a.bs;
+    fc.e4[0] = a.e4[0];
+    fc.e4[1] = a.e4[1];
+    fc.xbs = a.xbs;
+    return fc;
+}
+
+// ------------------------------------------------------------------------------------------
 // Variant 1: direct LDG.  CTA tile = WARPS * U * 32 chunks; warp w owns a contiguous run of
 // U*32 chunks of it; tiles are dealt blocked-cyclically so the grid sweeps the haystack as a
 // moving band (good for early exit and DRAM page locality).
@@ -39,9 +76,9 @@
 // CLAMP=false is the interior fast path (every load provably in range: plain base+immediate
 // addressing); CLAMP=true clamps each chunk index to the last loadable chunk (tail tiles).
 // Returns true when the early-exit test says this CTA can stop.
-template <int WS, bool BSZ, bool QZ, bool K1, int NE, int U, bool CLAMP>
+template <int WS, bool BSZ, bool QZ, bool K1, int XK, int U, bool CLAMP>
 __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restrict__ chunks, unsigned long long cw,
-                                         int lane, uint32_t f4, uint32_t l4, uint32_t bs, const uint32_t (&e4)[3])
+                                         int lane, const FilterConsts &fc, AdaptiveFilter &af)
 {
     // early exit: nothing at or right of this warp's first position can beat the current best
     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
@@ -51,32 +88,39 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
     const uint4 *pq = p + a.q;
     constexpr bool NEED_HI = !(BSZ && WS == 0); // second-anchor window spills into the following chunk
 
+    // The next chunk `nx` is part of the second-anchor window when QZ; otherwise only the extra
+    // anchors and the verify path read it, so it is fetched lazily (warp-uniform conditions).
+    constexpr bool NX_EAGER = QZ && !K1;
+    auto load_nx = [&](int u) -> uint4 {
+        if (CLAMP) {
+            const unsigned long long c = c0 + u * 32 + 1;
+            return ldg16(chunks + (c < last ? c : last));
+        }
+        return ldg16(p + u * 32 + 1);
+    };
     uint4 av[U], nx[U], lo[U], hi[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         if (CLAMP) {
             const unsigned long long c = c0 + u * 32;
             av[u] = ldg16(chunks + (c < last ? c : last));
-            nx[u] = K1 ? av[u] : ldg16(chunks + (c + 1 < last ? c + 1 : last));
         } else {
             av[u] = ldg16(p + u * 32);
-            nx[u] = K1 ? av[u] : ldg16(p + u * 32 + 1);
         }
+        nx[u] = NX_EAGER ? load_nx(u) : av[u];
     }
-    if (!K1) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (QZ) {
-                lo[u] = av[u];
-                hi[u] = nx[u];
-            } else if (CLAMP) {
-                const unsigned long long c = c0 + u * 32 + a.q;
-                lo[u] = ldg16(chunks + (c < last ? c : last));
-                hi[u] = NEED_HI ? ldg16(chunks + (c + 1 < last ? c + 1 : last)) : lo[u];
-            } else {
-                lo[u] = ldg16(pq + u * 32);
-                hi[u] = NEED_HI ? ldg16(pq + u * 32 + 1) : lo[u];
-            }
+    for (int u = 0; u < U; u++) {
+        if (K1 || QZ) {
+            lo[u] = av[u];
+            hi[u] = nx[u];
+        } else if (CLAMP) {
+            const unsigned long long c = c0 + u * 32 + a.q;
+            lo[u] = ldg16(chunks + (c < last ? c : last));
+            hi[u] = NEED_HI ? ldg16(chunks + (c + 1 < last ? c + 1 : last)) : lo[u];
+        } else {
+            lo[u] = ldg16(pq + u * 32);
+            hi[u] = NEED_HI ? ldg16(pq + u * 32 + 1) : lo[u];
         }
     }
     if (key) {
@@ -85,24 +129,33 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
             return true;
     }
     uint32_t fl[U];
-    uint32_t any = 0;
+    const bool extras = (XK != 0) && af.begin_tile(); // one step per warp per tile in this variant
+    if (!NX_EAGER && !K1 && extras) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        fl[u] = chunk_flag_x<WS, BSZ, K1, NE>(av[u], nx[u], lo[u], hi[u], f4, l4, bs, e4);
-        any |= fl[u];
+        for (int u = 0; u < U; u++)
+            nx[u] = load_nx(u);
     }
-    if (__any_sync(0xFFFFFFFFu, any != 0)) {
+    const uint32_t any = step_flags<WS, BSZ, K1, XK, U>(av, nx, lo, hi, fc, extras, fl);
+    const bool slow = __any_sync(0xFFFFFFFFu, any != 0);
+    if (XK != 0)
+        af.end_tile(extras, slow ? 4u : 0u);
+    if (slow) {
+        if (!NX_EAGER && !K1 && !extras) {
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                nx[u] = load_nx(u);
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const unsigned long long c = c0 + u * 32;
             if (fl[u] && (!CLAMP || c < a.n_chunks))
-                verify_chunk<WS, BSZ, K1, NE>(a, av[u], nx[u], lo[u], hi[u], c);
+                verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
         }
     }
     return false;
 }
 
-template <int WS, bool BSZ, bool QZ, bool K1, int NE, int U>
+template <int WS, bool BSZ, bool QZ, bool K1, int XK, int U>
 __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_constant__ ScanArgs a)
 {
     constexpr int WARPS = SS_LDG_THREADS / 32;
@@ -120,18 +173,18 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
         if (lim < n_interior)
             n_interior = lim;
     }
-    const uint32_t f4 = a.f4, l4 = a.l4, bs = a.bs;
-    const uint32_t e4[3] = {a.e4[0], a.e4[1], a.e4[2]};
+    const FilterConsts fc = load_filter_consts(a);
+    AdaptiveFilter af;
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
         bool stop;
         if (tile < n_interior) {
-            stop = ldg_step<WS, BSZ, QZ, K1, NE, U, false>(a, chunks, cw, lane, f4, l4, bs, e4);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af);
         } else {
             if (cw >= a.n_chunks)
                 continue; // this warp's run holds no start position (warp-uniform)
-            stop = ldg_step<WS, BSZ, QZ, K1, NE, U, true>(a, chunks, cw, lane, f4, l4, bs, e4);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af);
         }
         if (stop)
             break; // every later tile of this CTA is further right still
@@ -146,9 +199,9 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
 // SWAR filter out of shared memory, and release the stage through its "empty" mbarrier.
 // Dynamic smem layout: [stages][stage_stride] data, then full[stages], empty[stages] mbarriers,
 // then one uint32 "valid" word per stage (0 = producer stopped: early exit or end of work).
-template <int WS, bool BSZ, bool QZ, bool K1, int NE, int TILE>
-__global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3)) scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages,
-                                                                  uint32_t stage_stride, uint32_t halo)
+template <int WS, bool BSZ, bool QZ, bool K1, int XK, int TILE>
+__global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
+    scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages, uint32_t stage_stride, uint32_t halo)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int CW = SS_TMA_CONSUMER_WARPS;
@@ -213,8 +266,8 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3)) scan_
         }
     } else {
         // ===== consumers =====
-        const uint32_t f4 = a.f4, l4 = a.l4, bs = a.bs;
-        const uint32_t e4[3] = {a.e4[0], a.e4[1], a.e4[2]};
+        const FilterConsts fc = load_filter_consts(a);
+        AdaptiveFilter af;
         const uint32_t qb = a.q * 16u;
         int s = 0;
         uint32_t ph = 0;
@@ -224,44 +277,58 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3)) scan_
                 break;
             const uint8_t *st = smem + (size_t)s * stage_stride;
             const unsigned long long tile_c0 = tile * (unsigned long long)TILE_CHUNKS;
+            constexpr int STEPS = WARP_CHUNKS / (32 * U);
+            static_assert(STEPS == 1 || STEPS == 2 || STEPS == 4, "trip share is counted in quarters");
+            const bool extras = (XK != 0) && af.begin_tile();
+            uint32_t trips = 0;
 #pragma unroll 1
-            for (int step = 0; step < WARP_CHUNKS / (32 * U); step++) {
+            for (int step = 0; step < STEPS; step++) {
                 const uint32_t lc0 = (uint32_t)warp * WARP_CHUNKS + step * (32 * U) + lane; // chunk within tile
+                // `nx` (the next chunk) is fetched lazily unless it is part of the second-anchor window
+                constexpr bool NX_EAGER = QZ && !K1;
                 uint4 av[U], nx[U], lo[U], hi[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     av[u] = lds16(st + (lc0 + u * 32) * 16u);
-                    nx[u] = K1 ? av[u] : lds16(st + (lc0 + u * 32) * 16u + 16u);
+                    nx[u] = NX_EAGER ? lds16(st + (lc0 + u * 32) * 16u + 16u) : av[u];
                 }
-                if (!K1) {
 #pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        if (QZ) {
-                            lo[u] = av[u];
-                            hi[u] = nx[u];
-                        } else {
-                            const uint32_t b = (lc0 + u * 32) * 16u + qb;
-                            lo[u] = lds16(st + b);
-                            hi[u] = NEED_HI ? lds16(st + b + 16u) : lo[u];
-                        }
+                for (int u = 0; u < U; u++) {
+                    if (K1 || QZ) {
+                        lo[u] = av[u];
+                        hi[u] = nx[u];
+                    } else {
+                        const uint32_t b = (lc0 + u * 32) * 16u + qb;
+                        lo[u] = lds16(st + b);
+                        hi[u] = NEED_HI ? lds16(st + b + 16u) : lo[u];
                     }
                 }
                 uint32_t fl[U];
-                uint32_t any = 0;
+                if (!NX_EAGER && !K1 && extras) {
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    fl[u] = chunk_flag_x<WS, BSZ, K1, NE>(av[u], nx[u], lo[u], hi[u], f4, l4, bs, e4);
-                    any |= fl[u];
+                    for (int u = 0; u < U; u++)
+                        nx[u] = lds16(st + (lc0 + u * 32) * 16u + 16u);
                 }
-                if (__any_sync(0xFFFFFFFFu, any != 0)) {
+                const uint32_t any = step_flags<WS, BSZ, K1, XK, U>(av, nx, lo, hi, fc, extras, fl);
+                const bool slow = __any_sync(0xFFFFFFFFu, any != 0);
+                if (XK != 0)
+                    trips += slow ? 1u : 0u;
+                if (slow) {
+                    if (!NX_EAGER && !K1 && !extras) {
+#pragma unroll
+                        for (int u = 0; u < U; u++)
+                            nx[u] = lds16(st + (lc0 + u * 32) * 16u + 16u);
+                    }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const unsigned long long c = tile_c0 + lc0 + u * 32;
                         if (fl[u] && c < a.n_chunks)
-                            verify_chunk<WS, BSZ, K1, NE>(a, av[u], nx[u], lo[u], hi[u], c);
+                            verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
                     }
                 }
             }
+            if (XK != 0)
+                af.end_tile(extras, trips * (4u / STEPS));
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&empty[s]);

@@ -4,9 +4,9 @@
 #include "scan_long.cuh"
 #include "ss_host.h"
 
-// Expands to a function `NAME(ws, bsz, qz, k1, ne)` returning the kernel KERNEL<WS,BSZ,QZ,K1,NE,LAST>.
+// Expands to a function `NAME(ws, bsz, qz, k1, xk)` returning the kernel KERNEL<WS,BSZ,QZ,K1,XK,LAST>.
 #define SS_TAB_NE(KERNEL, FN, LAST, WS, BSZ, QZ)                                                                     \
-    switch (ne) {                                                                                                    \
+    switch (xk) {                                                                                                    \
     case 0: return (FN)KERNEL<WS, BSZ, QZ, false, 0, LAST>;                                                          \
     case 1: return (FN)KERNEL<WS, BSZ, QZ, false, 1, LAST>;                                                          \
     case 2: return (FN)KERNEL<WS, BSZ, QZ, false, 2, LAST>;                                                          \
@@ -25,7 +25,7 @@
         SS_TAB_QZ(KERNEL, FN, LAST, WS, false)                                                                       \
     }
 #define SS_DEFINE_TABLE(NAME, KERNEL, FN, LAST)                                                                      \
-    FN NAME(int ws, bool bsz, bool qz, bool k1, int ne)                                                              \
+    FN NAME(int ws, bool bsz, bool qz, bool k1, int xk)                                                              \
     {                                                                                                                \
         if (k1)                                                                                                      \
             return (FN)KERNEL<0, true, true, true, 0, LAST>;                                                         \

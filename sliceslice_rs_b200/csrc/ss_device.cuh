@@ -44,8 +44,9 @@ struct ScanArgs {
     uint32_t f4;   // needle[0] splatted x4
     uint32_t l4;   // needle[pos] splatted x4
     uint32_t bs;   // 8 * (pos % 4): bit shift of the second-anchor stream inside a word
-    uint32_t ne;   // extra word-aligned anchors in use (needle offsets 4, 8, 12), 0..3
-    uint32_t e4[3]; // needle[4], needle[8], needle[12] splatted x4
+    uint32_t xk;   // extra-anchor kind the kernel was instantiated with (see filter_word)
+    uint32_t e4[2]; // extra anchor bytes splatted x4
+    uint32_t xbs;  // xk == 3: 8 * needle offset (1..3) of the unaligned extra anchor
     uint8_t needle_inline[SS_INLINE_NEEDLE_MAX]; // first min(k, 64) needle bytes
 };
 
@@ -107,39 +108,90 @@ __device__ __forceinline__ uint32_t window_word_rt(const uint4 &lo, const uint4 
 }
 
 // The filter word for 4 start positions (word j of a chunk):
-//   zero byte <=> hay[i] == needle[0] && hay[i+pos] == needle[pos] && hay[i+4e] == needle[4e] (e = 1..NE)
+//   zero byte <=> hay[i] == needle[0] && hay[i+pos] == needle[pos] [&& extra anchors]
 // The first two terms are the reference's two anchors (VectorHash first/last, src/lib.rs:166-178,
-// :207-214).  The NE extra anchors sit at needle offsets 4, 8, 12: those byte streams are word-aligned
-// with the first one, so each costs one LOP3 per word and no shift.  They only make the filter more
-// selective (fewer trips to the divergent verify path on natural text); a real match always passes.
+// :207-214).  Extra anchors (XK) only make the filter more selective -- fewer trips to the divergent
+// verify path on natural text; a real match always passes, so results never change:
+//   XK = 0  none
+//   XK = 1  needle[4]             word-aligned with the first stream: one LOP3 per word, no shift
+//   XK = 2  needle[4], needle[8]  two LOP3 per word
+//   XK = 3  needle[xo], xo in 1..3 (short needles): one funnel shift + one LOP3 per word
 //   av : haystack bytes [16c, 16c+16)      nx : the next 16 bytes [16c+16, 16c+32)
 //   lo : haystack bytes [16(c+q), +16)     hi : the 16 after lo (lo/hi == av/nx when q == 0)
-template <int WS, bool BSZ, bool K1, int NE>
+struct FilterConsts {
+    uint32_t f4, l4, bs; // needle[0] x4, needle[pos] x4, 8 * (pos % 4)
+    uint32_t e4[2];      // extra anchor bytes x4
+    uint32_t xbs;        // XK == 3: 8 * xo
+};
+
+template <int WS, bool BSZ, bool K1, int XK>
 __device__ __forceinline__ uint32_t filter_word(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi,
-                                                int j, uint32_t f4, uint32_t l4, uint32_t bs, const uint32_t (&e4)[3])
+                                                int j, const FilterConsts &fc)
 {
     const uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
-    uint32_t x = w[j] ^ f4;
+    uint32_t x = w[j] ^ fc.f4;
     if (!K1) {
-        x |= window_word_rt<WS, BSZ>(lo, hi, j, bs) ^ l4;
-#pragma unroll
-        for (int e = 0; e < NE; e++)
-            x |= w[j + e + 1] ^ e4[e];
+        x |= window_word_rt<WS, BSZ>(lo, hi, j, fc.bs) ^ fc.l4;
+        if (XK == 1 || XK == 2)
+            x |= w[j + 1] ^ fc.e4[0];
+        if (XK == 2)
+            x |= w[j + 2] ^ fc.e4[1];
+        if (XK == 3)
+            x |= __funnelshift_r(w[j], w[j + 1], fc.xbs) ^ fc.e4[0];
     }
     return x;
 }
 
 // Candidate test for the 16 start positions of one chunk: non-zero iff some position MAY pass the filter.
-template <int WS, bool BSZ, bool K1, int NE>
+template <int WS, bool BSZ, bool K1, int XK>
 __device__ __forceinline__ uint32_t chunk_flag_x(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi,
-                                                 uint32_t f4, uint32_t l4, uint32_t bs, const uint32_t (&e4)[3])
+                                                 const FilterConsts &fc)
 {
     uint32_t acc = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        acc |= swar_zero_term(filter_word<WS, BSZ, K1, NE>(av, nx, lo, hi, j, f4, l4, bs, e4));
+        acc |= swar_zero_term(filter_word<WS, BSZ, K1, XK>(av, nx, lo, hi, j, fc));
     return acc & 0x80808080u;
 }
+
+// Per-warp, per-tile switch between the plain two-anchor filter and the one with extra anchors.
+// The plain filter is cheapest when candidates are rare (random bytes); on natural text a common
+// anchor pair sends almost every warp step through the verify path and the extra anchors pay for
+// themselves.  `s` (0..4) is the share of a tile's steps that took the verify path, in quarters.
+//   PLAIN  (period == 0): est <- 3/4 est + 4 s settles at 16 s; two consecutive all-trip tiles (or a
+//          sustained trip rate above ~40%) reach 24 and switch the extras on.
+//   EXTRAS (period != 0): every `period`-th tile runs the plain filter as a probe.  A probe with fewer
+//          than half of its steps tripping returns to PLAIN at once; otherwise the period doubles
+//          (4, 8, ... 64 tiles), so on text the probes cost ~2% of the tiles.
+// The bookkeeping runs once per tile, outside the step loop.  All fields are warp-uniform.
+struct AdaptiveFilter {
+    uint32_t est = 0;
+    uint32_t period = 0;
+    uint32_t left = 0;
+    __device__ __forceinline__ bool begin_tile()
+    {
+        if (period == 0u || left == 0u)
+            return false;
+        left--;
+        return true;
+    }
+    __device__ __forceinline__ void end_tile(bool used_extras, uint32_t s)
+    {
+        if (used_extras)
+            return;
+        if (period == 0u) {
+            est = est - (est >> 2) + 4u * s;
+            if (est >= 24u)
+                period = left = 4u;
+        } else if (s >= 2u) {
+            period = period < 64u ? period * 2u : 64u;
+            left = period;
+        } else {
+            period = 0u;
+            est = 0u;
+        }
+    }
+};
 
 // Two-anchor form with a compile-time byte shift (used by the batched multi-needle kernel).
 template <int R, bool K1>
@@ -196,15 +248,18 @@ static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const u
 // alive start position; each round slides the window by one byte and ANDs in the exact compare with
 // the next needle byte for all 16 positions at once.  Natural-text false candidates die in the first
 // round or two.  Survivors (17 bytes equal) of longer needles finish from global memory.
-template <int WS, bool BSZ, bool K1, int NE>
+template <int WS, bool BSZ, bool K1>
 __device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx, uint4 lo, uint4 hi,
                                           unsigned long long chunk)
 {
-    uint32_t e4[3] = {a.e4[0], a.e4[1], a.e4[2]};
+    FilterConsts fc;
+    fc.f4 = a.f4;
+    fc.l4 = a.l4;
+    fc.bs = a.bs;
     uint32_t z[4];
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, NE>(av, nx, lo, hi, j, a.f4, a.l4, a.bs, e4));
+        z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, j, fc));
     if (!K1) {
         uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
         const uint32_t jmax = a.k - 1 < 16u ? a.k - 1 : 16u;

@@ -12,7 +12,7 @@ struct SsScanTuning {
     int unroll = 0;      // LDG: chunks per lane per step (1, 2, 4); 0 auto
     int tile_kib = 0;    // TMA: 16 or 32; 0 auto
     int stages = 0;      // TMA ring depth; 0 auto
-    int extra_anchors = -1; // word-aligned extra anchors (0..3); -1 auto
+    int extra_anchors = -1; // 0 = never use extra anchors, -1 = auto (adaptive, see AdaptiveFilter)
 };
 
 struct SsDeviceInfo {
@@ -26,10 +26,10 @@ struct SsDeviceInfo {
 using SsLdgFn = void (*)(const ScanArgs);
 using SsTmaFn = void (*)(const ScanArgs, int, uint32_t, uint32_t);
 // kernel tables, one translation unit each (scan_ldg_u1.cu, scan_ldg_u4.cu, scan_tma_16.cu, scan_tma_32.cu)
-SsLdgFn ss_table_ldg_u1(int ws, bool bsz, bool qz, bool k1, int ne);
-SsLdgFn ss_table_ldg_u4(int ws, bool bsz, bool qz, bool k1, int ne);
-SsTmaFn ss_table_tma_16(int ws, bool bsz, bool qz, bool k1, int ne);
-SsTmaFn ss_table_tma_32(int ws, bool bsz, bool qz, bool k1, int ne);
+SsLdgFn ss_table_ldg_u1(int ws, bool bsz, bool qz, bool k1, int xk);
+SsLdgFn ss_table_ldg_u4(int ws, bool bsz, bool qz, bool k1, int xk);
+SsTmaFn ss_table_tma_16(int ws, bool bsz, bool qz, bool k1, int xk);
+SsTmaFn ss_table_tma_32(int ws, bool bsz, bool qz, bool k1, int xk);
 
 uint64_t ss_host_launch_count();
 void ss_host_count_launch(uint64_t n);

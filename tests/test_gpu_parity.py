@@ -237,9 +237,9 @@ def test_randomized_differential(alphabet, variant):
         s.close()
 
 
-@pytest.mark.parametrize("ne", [0, 1, 2, 3])
+@pytest.mark.parametrize("ne", [0, 1])
 def test_extra_anchor_settings_do_not_change_results(ne, variant):
-    # the word-aligned extra anchors (needle offsets 4, 8, 12) only thin out the candidates
+    # extra anchors (adaptive, see AdaptiveFilter in ss_device.cuh) only thin out the candidates
     ss.set_extra_anchors(ne)
     try:
         rng = random.Random(500 + ne)

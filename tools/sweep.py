@@ -58,7 +58,7 @@ def main():
             tt = [int(x) for x in t.split(",")]
             ss.set_scan_tuning(*tt[:4])
             ss.set_extra_anchors(tt[4] if len(tt) > 4 else -1)
-            for _ in range(2):
+            for _ in range(6):
                 s.find_in_async(hay, res, ws)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
