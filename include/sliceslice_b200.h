@@ -136,6 +136,18 @@ int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t 
 int ss_b200_find_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base_offset,
                                  size_t start_limit, void *workspace, uint64_t *d_result, void *stream);
 
+/* Many-haystack mode, stream-ordered: ONE needle against a device-resident SET of haystacks in a
+ * single pass at the long-scan rate (the set is scanned as one blob; a match counts for haystack h
+ * only if it lies wholly inside it).  Per haystack the result is search_in() of src/x86.rs:523.
+ *   d_blob, blob_len  concatenated haystack bytes in device memory
+ *   d_offsets         n_haystacks+1 uint64 in device memory, d_offsets[0] == 0, d_offsets[n] == blob_len
+ *   d_flags           n_haystacks uint8 in device memory: set to 1/0 per haystack
+ *   workspace         32 bytes of device memory, zero when enqueued (left zero again)
+ * Multi-GPU: each rank holds a subset of the haystacks and writes its slice of one global flag
+ * array; the slices are OR-ed with ncclAllReduce(ncclMax, ncclUint8) (NCCL has no bitwise OR). */
+int ss_b200_search_many_async(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets,
+                              size_t n_haystacks, size_t blob_len, uint8_t *d_flags, void *workspace, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* Batched modes (north-star "batched many-haystack mode"; workloads:
  * bench/benches/i386.rs:118-131 short sweep, :246-257 all needles over one

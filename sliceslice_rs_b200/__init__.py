@@ -29,7 +29,7 @@ import numpy as np
 
 __all__ = ["DynamicB200Searcher", "B200Searcher", "DeviceHaystack", "SearcherPanic", "B200Error", "lib",
            "NPOS", "DEVICE_NONE", "fill_random", "fill_tiled", "set_scan_variant", "set_scan_tuning",
-           "launch_count", "Batch", "set_extra_anchors"]
+           "launch_count", "Batch", "set_extra_anchors", "HaystackSet"]
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsliceslice_b200.so")
@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         "ss_b200_search_in_host": (i32, [vp, vp, sz, C.POINTER(C.c_uint8)]),
         "ss_b200_find_in_host": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "ss_b200_find_in_device_async": (i32, [vp, vp, sz, u64, sz, vp, vp, vp]),
+        "ss_b200_search_many_async": (i32, [vp, vp, vp, sz, sz, vp, vp, vp]),
         "ss_b200_batch_create": (i32, [vp, vp, sz, vp, vp, sz, pp]),
         "ss_b200_batch_free": (None, [vp]),
         "ss_b200_batch_search_pairs": (i32, [vp, vp, vp, sz, vp, vp]),
@@ -258,6 +259,21 @@ class _SearcherBase:
         _check(lib().ss_b200_find_in_device_async(self._s, hay.data_ptr(), hay.numel(), int(base_offset), lim,
                                                   workspace.data_ptr(), result.data_ptr(), sp))
 
+    def search_many_async(self, hayset: "HaystackSet", flags=None, stream=None):
+        """One pass over a device-resident set of haystacks (``ss_b200_search_many_async``):
+        ``flags[h] = search_in(haystack h)`` as uint8.  Returns the flags tensor (stream-ordered)."""
+        import torch
+
+        if flags is None:
+            flags = torch.empty(len(hayset), dtype=torch.uint8, device=hayset.blob.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(hayset.blob.device)
+        sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        _check(lib().ss_b200_search_many_async(self._s, hayset.blob.data_ptr(), hayset.offsets.data_ptr(),
+                                               len(hayset), hayset.blob_len, flags.data_ptr(),
+                                               hayset.workspace.data_ptr(), sp))
+        return flags
+
     def close(self) -> None:
         if self._s:
             lib().ss_b200_searcher_free(self._s)
@@ -278,6 +294,23 @@ class DynamicB200Searcher(_SearcherBase):
 class B200Searcher(_SearcherBase):
     """Drop-in for ``sliceslice::x86::Avx2Searcher`` (src/x86.rs:266-383): empty needle panics."""
     _STRICT = True
+
+
+class HaystackSet:
+    """A set of haystacks resident in HBM as one blob + uint64 offsets (many-haystack mode)."""
+
+    def __init__(self, haystacks, device="cuda"):
+        import torch
+
+        blob, off = _csr(haystacks)
+        self.n = len(haystacks)
+        self.blob_len = int(off[-1])
+        self.blob = torch.from_numpy(blob.copy()).to(device)
+        self.offsets = torch.from_numpy(off.astype(np.int64)).to(device)
+        self.workspace = torch.zeros(32, dtype=torch.uint8, device=device)
+
+    def __len__(self) -> int:
+        return self.n
 
 
 class Batch:

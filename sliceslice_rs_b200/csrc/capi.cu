@@ -365,6 +365,52 @@ extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const voi
     return SS_B200_OK;
 }
 
+// Many-haystack mode: one needle against a device-resident set of haystacks in one pass.
+__global__ void fill_flags_kernel(uint8_t *flags, unsigned long long n, uint8_t v)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        flags[i] = v;
+}
+
+extern "C" int ss_b200_search_many_async(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets,
+                                         size_t n_haystacks, size_t blob_len, uint8_t *d_flags, void *workspace,
+                                         void *stream)
+{
+    if (!s || !d_offsets || !d_flags || !workspace || (blob_len && !d_blob))
+        return SS_B200_E_ARG;
+    if (n_haystacks == 0)
+        return SS_B200_OK;
+    const size_t k = s->needle.size();
+    if (k > 0xFFFFFFFFull)
+        return SS_B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    // k == 0: every haystack matches (N0, src/x86.rs:500); otherwise start from "not found"
+    const unsigned blocks = (unsigned)((n_haystacks + 255) / 256 < (size_t)dev.sm_count * 8 ? (n_haystacks + 255) / 256
+                                                                                             : (size_t)dev.sm_count * 8);
+    fill_flags_kernel<<<blocks, 256, 0, st>>>(d_flags, n_haystacks, k == 0 ? 1 : 0);
+    ss_host_count_launch(1);
+    SS_CUDA(cudaGetLastError());
+    if (k == 0 || blob_len < k)
+        return SS_B200_OK;
+    ScanArgs a;
+    rc = build_args(s, d_blob, blob_len, 0, (size_t)-1, dev.device, a);
+    if (rc != SS_B200_OK)
+        return rc;
+    a.ws = (SsWorkspace *)workspace;
+    a.out = (unsigned long long *)((uint8_t *)workspace + 16); // scratch result slot, unused by callers
+    a.out_seq = nullptr;
+    a.seg_off = (const unsigned long long *)d_offsets;
+    a.seg_flags = d_flags;
+    a.n_seg = n_haystacks;
+    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
+    return SS_B200_OK;
+}
+
 // One synchronous scan of device memory through the thread's context.
 static int find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset)
 {

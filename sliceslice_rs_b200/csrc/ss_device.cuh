@@ -47,6 +47,11 @@ struct ScanArgs {
     uint32_t xk;   // extra-anchor kind the kernel was instantiated with (see filter_word)
     uint32_t e4[2]; // extra anchor bytes splatted x4
     uint32_t xbs;  // xk == 3: 8 * needle offset (1..3) of the unaligned extra anchor
+    // many-haystack mode (nullptr otherwise): hay is the concatenation of n_seg haystacks, haystack h
+    // = bytes [seg_off[h], seg_off[h+1]) with seg_off[0] == 0; seg_flags[h] <- 1 when it contains the needle
+    const unsigned long long *seg_off;
+    uint8_t *seg_flags;
+    unsigned long long n_seg;
     uint8_t needle_inline[SS_INLINE_NEEDLE_MAX]; // first min(k, 64) needle bytes
 };
 
@@ -242,6 +247,22 @@ static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const u
     return true;
 }
 
+// Many-haystack mode: mark the haystack that wholly contains the match at blob position i.
+static __device__ __noinline__ void segment_hit(const ScanArgs &a, unsigned long long i)
+{
+    // h = last segment with seg_off[h] <= i
+    unsigned long long lo = 0, hi = a.n_seg; // invariant: seg_off[lo] <= i < seg_off[hi]
+    while (hi - lo > 1) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (__ldg(a.seg_off + mid) <= i)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    if (i + a.k <= __ldg(a.seg_off + lo + 1))
+        a.seg_flags[lo] = 1;
+}
+
 // Hit path for one chunk whose SWAR flag fired -- the ctz loop + memcmp of src/lib.rs:216-248, done
 // without touching memory: the lane already holds the 32 haystack bytes [16c, 16c+32) in registers,
 // which cover needle bytes 0..16 of every start position of the chunk.  `z` keeps one bit per still-
@@ -290,6 +311,12 @@ __device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx,
             if (i < 0 || (unsigned long long)i >= a.end)
                 continue;
             if (K1 || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
+                if (a.seg_off) {
+                    // many-haystack mode: the blob is a concatenation of haystacks; a match counts for
+                    // haystack h iff it lies entirely inside [seg_off[h], seg_off[h+1]).  No early exit.
+                    segment_hit(a, (unsigned long long)i);
+                    continue;
+                }
                 atomicMax(&a.ws->key, ~(unsigned long long)i);
                 __threadfence();
                 return; // ascending order: later positions of this chunk cannot be smaller

@@ -103,3 +103,30 @@ class ShardedSearch:
 
     def search(self, searcher) -> bool:
         return self.find(searcher) is not None
+
+
+class ShardedHaystackSet:
+    """Many-haystack mode over several GPUs: haystack index ranges per rank (length-balanced,
+    :func:`partition_by_length`), needles replicated, one global uint8 flag array whose per-rank
+    slices are OR-ed with ``all_reduce(MAX)``."""
+
+    def __init__(self, haystacks, rank: int = 0, world: int = 1, group=None, device="cuda"):
+        import torch
+
+        from . import HaystackSet
+
+        self.total = len(haystacks)
+        self.group = group
+        self.lo, self.hi = partition_by_length([len(h) for h in haystacks], world)[rank]
+        self.local = HaystackSet(haystacks[self.lo:self.hi], device=device)
+        self.flags = torch.zeros(self.total, dtype=torch.uint8, device=device)
+
+    def search_async(self, searcher, stream=None):
+        """flags[h] = searcher.search_in(haystack h) for every haystack of the global set."""
+        self.flags.zero_()
+        if self.hi > self.lo:
+            searcher.search_many_async(self.local, self.flags[self.lo:self.hi], stream=stream)
+        return reduce_flags(self.flags, self.group)
+
+    def search(self, searcher):
+        return self.search_async(searcher).cpu().numpy().astype(bool)

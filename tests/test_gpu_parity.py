@@ -428,6 +428,44 @@ def test_sharded_logic_on_one_gpu(world, variant):
         host = oracle.fill_random(0, n, SEED_HAY)
 
 
+def test_many_haystack_mode_vs_oracle(sorted_words, i386, variant):
+    # one needle against a device-resident SET of haystacks in one pass; per haystack == search_in()
+    rng = random.Random(21)
+    hays = list(sorted_words) + [b"", b"a", b"", i386[:70000], b"xyz" * 5000, b"", i386[300000:340000], b"q"]
+    rng.shuffle(hays)
+    hs = ss.HaystackSet(hays)
+    needles = [b"", b"a", b"e", b"th", b"the", b"tion", b"segment", b"ipsum", b"zq", b"xyzx", b"interrupt",
+               b"descriptor table", i386[1000:1040], i386[69990:70010], i386[339980:340000], b"q"]
+    for nd in needles:
+        for pos in sorted({0, len(nd) // 2, max(len(nd) - 1, 0)}):
+            s = ss.DynamicB200Searcher.with_position(nd, pos) if nd else ss.DynamicB200Searcher.new(nd)
+            got = s.search_many_async(hs).cpu().numpy().astype(bool)
+            exp = oracle.pairs([nd], hays, np.zeros(len(hays), np.uint32), np.arange(len(hays), dtype=np.uint32))
+            assert np.array_equal(got, exp != oracle.NPOS), nd
+            assert got.tolist() == [h.find(nd) >= 0 for h in hays]
+            s.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_sharded_haystack_set_on_one_gpu(world, sorted_words):
+    # emulate `world` ranks on one device: OR of the per-rank flag arrays == the global answer
+    from sliceslice_rs_b200.sharded import ShardedHaystackSet
+
+    hays = sorted_words[::3] + [b"", b"the quick brown fox jumps over the lazy dog" * 300]
+    for nd in (b"the", b"ing", b"ipsum", b"o"):
+        s = ss.DynamicB200Searcher.new(nd)
+        acc = np.zeros(len(hays), bool)
+        covered = 0
+        for r in range(world):
+            sh = ShardedHaystackSet(hays, rank=r, world=world)
+            covered += sh.hi - sh.lo
+            got = sh.search(s)
+            assert not got[: sh.lo].any() and not got[sh.hi:].any()  # a rank only sets its own slice
+            acc |= got
+        assert covered == len(hays)
+        assert acc.tolist() == [h.find(nd) >= 0 for h in hays]
+
+
 def test_const_handles_from_many_threads(i386, words):
     # reference searchers are Send + Sync (src/x86.rs:266-271)
     hs = ss.DeviceHaystack.upload(i386)
