@@ -167,7 +167,7 @@ __device__ __forceinline__ uint32_t chunk_flag_x(const uint4 &av, const uint4 &n
 //          sustained trip rate above ~40%) reach 24 and switch the extras on.
 //   EXTRAS (period != 0): every `period`-th tile runs the plain filter as a probe.  A probe with fewer
 //          than half of its steps tripping returns to PLAIN at once; otherwise the period doubles
-//          (4, 8, ... 64 tiles), so on text the probes cost ~2% of the tiles.
+//          (4, 8, ... 128 tiles), so on text the probes cost ~1% of the tiles.
 // The bookkeeping runs once per tile, outside the step loop.  All fields are warp-uniform.
 struct AdaptiveFilter {
     uint32_t est = 0;
@@ -189,7 +189,7 @@ struct AdaptiveFilter {
             if (est >= 24u)
                 period = left = 4u;
         } else if (s >= 2u) {
-            period = period < 64u ? period * 2u : 64u;
+            period = period < 128u ? period * 2u : 128u;
             left = period;
         } else {
             period = 0u;
