@@ -101,6 +101,25 @@ class ShardedSearch:
         v = int(self.find_async(searcher).item())
         return None if v == DEVICE_NONE else v
 
+    def find_many(self, searchers) -> List[Optional[int]]:
+        """Pipelined batch of independent searches over the same sharded haystack: the 8-byte
+        MIN-allreduce of search i runs on NCCL's stream while search i+1 already scans, so the
+        exchange never stalls the scan stream.  Returns the global leftmost offsets."""
+        import torch
+        import torch.distributed as dist
+
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        results = torch.full((len(searchers),), DEVICE_NONE, dtype=torch.int64, device=self.shard.device)
+        works = []
+        for i, s in enumerate(searchers):
+            s.find_in_async(self.shard, results[i:i + 1], self.workspace, base_offset=self.start,
+                            start_limit=self.owned)
+            if multi:
+                works.append(dist.all_reduce(results[i:i + 1], op=dist.ReduceOp.MIN, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+        return [None if v == DEVICE_NONE else v for v in results.tolist()]
+
     def search(self, searcher) -> bool:
         return self.find(searcher) is not None
 
