@@ -36,6 +36,40 @@ def binary(kats):
     return exe
 
 
+@pytest.fixture(scope="module")
+def grep_binary():
+    from sliceslice_rs_b200 import build
+
+    lib = build.build()
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "grep")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "grep.cpp"), "-o", exe, lib, f"-Wl,-rpath,{os.path.dirname(lib)}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_grep_example_builds_and_rejects_bad_arguments(grep_binary):
+    r = subprocess.run([grep_binary], capture_output=True, text=True)
+    assert r.returncode == 101 and "<backend> <needle> <file>" in r.stderr
+    r = subprocess.run([grep_binary, "avx512", "x", os.path.join(ROOT, "data", "needle")], capture_output=True, text=True)
+    assert r.returncode == 101 and "Invalid backend" in r.stderr
+    # the empty needle panics for the strict searcher before any device work (src/x86.rs:285,300)
+    r = subprocess.run([grep_binary, "b200", "", os.path.join(ROOT, "data", "needle")], capture_output=True, text=True)
+    assert r.returncode == 101 and "panicked" in r.stderr
+
+
+@pytest.mark.gpu
+def test_grep_example_on_i386(grep_binary):
+    # examples/grep.rs:42-57 output format
+    f = os.path.join(ROOT, "data", "i386.txt")
+    for backend in ("b200", "DynamicB200"):
+        r = subprocess.run([grep_binary, backend, "segmentation", f], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.strip() == f'Searching for segmentation in "{f}": true', r.stdout + r.stderr
+        r = subprocess.run([grep_binary, backend, "ipsum", f], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.strip().endswith(": false")
+
+
 def test_cpp_mirror_constructor_contract(binary):
     r = subprocess.run([binary, "ctor"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -189,6 +189,27 @@ def test_pairs_mode_vs_oracle(sorted_words):
     assert np.array_equal(bits.astype(bool), exp != oracle.NPOS)
 
 
+def test_random_bench_size_grid(variant):
+    # bench/benches/random.rs:12-99: prefixes of data/needle in prefixes of data/haystack for the
+    # sizes {1,5,10,20,50,100,1000}, every needle size against every not-smaller haystack size (28 pairs)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    haystack = open(os.path.join(root, "data", "haystack"), "rb").read()
+    needle = open(os.path.join(root, "data", "needle"), "rb").read()
+    sizes = [1, 5, 10, 20, 50, 100, 1000]
+    found = []
+    for i, ns in enumerate(sizes):
+        nd = needle[:ns]
+        s = ss.DynamicB200Searcher.new(nd)
+        for hsz in sizes[i:]:
+            h = haystack[:hsz]
+            got = s.find_in(ss.DeviceHaystack.upload(h))
+            assert got == oracle.find(h, nd) == _expect(h, nd), (ns, hsz)
+            assert s.search_in(h) is (got is not None)  # host-slice entry
+            if got is not None:
+                found.append((ns, hsz))
+    assert found == [(1, 100), (1, 1000)]  # the only true pairs
+
+
 # ------------------------------------------------------------------------------------------
 # offset-pinning and randomized differential tests
 

@@ -1,6 +1,7 @@
 """CPU tests: pin the oracle (C restatement of DynamicAvx2Searcher) against the reference's
 own golden vectors (tests/golden/kats.json, corpus.json) and against independent voices."""
 import hashlib
+import os
 import random
 
 import numpy as np
@@ -127,3 +128,19 @@ def test_generators_are_deterministic():
     assert 0xFF not in a
     t = oracle.fill_tiled(5, 20, b"abcdefg")
     assert bytes(t) == (b"abcdefg" * 5)[5:25]
+
+
+def test_random_bench_size_grid():
+    # bench/benches/random.rs:12-99 workload: only needle[..1] in haystack[..100] / [..1000] match
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    haystack = open(os.path.join(root, "data", "haystack"), "rb").read()
+    needle = open(os.path.join(root, "data", "needle"), "rb").read()
+    sizes = [1, 5, 10, 20, 50, 100, 1000]
+    found = []
+    for i, ns in enumerate(sizes):
+        for hsz in sizes[i:]:
+            r = oracle.find(haystack[:hsz], needle[:ns])
+            assert r == (None if haystack[:hsz].find(needle[:ns]) < 0 else haystack[:hsz].find(needle[:ns]))
+            if r is not None:
+                found.append((ns, hsz))
+    assert found == [(1, 100), (1, 1000)]
