@@ -56,6 +56,9 @@ def parse_args():
     p.add_argument("--e2e-steps", type=int, default=5)
     p.add_argument("--e2e-gib", type=float, default=0.0, help="host haystack GiB per GPU (0 = same as --gib)")
     p.add_argument("--cpu-sample-gib", type=float, default=1.0)
+    p.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                   help="N > 1: how the per-shard first offsets are MIN-reduced (NCCL all_reduce, or stores into "
+                        "peer mailboxes fused into the scan epilogue)")
     p.add_argument("--no-extras", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -355,7 +358,12 @@ def main():
     shard = torch.empty(span, dtype=torch.uint8, device="cuda")
     ss.fill_tiled(shard, start, src)
     searcher = ss.DynamicB200Searcher.new(needle)
-    ws = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    peer = None
+    if world > 1 and args.exchange == "peer":
+        from sliceslice_rs_b200.sharded import PeerExchange
+
+        peer = PeerExchange()
     torch.cuda.synchronize()
 
     # One result slot per step: consecutive searches are independent, so the 8-byte MIN-allreduce of
@@ -368,6 +376,12 @@ def main():
     def step(i, ev_a=None, ev_b=None):
         if ev_a is not None:
             ev_a.record()
+        if peer is not None:
+            # scan + exchange in one call: the scan's last CTA stores into every rank's mailbox
+            peer.find_async(searcher, shard, start, owned, ws, results[i:i + 1])
+            if ev_b is not None:
+                ev_b.record()
+            return
         searcher.find_in_async(shard, results[i:i + 1], ws, base_offset=start, start_limit=owned)
         if ev_b is not None:
             ev_b.record()
@@ -481,9 +495,12 @@ def main():
                 "workload": f"i386 long-haystack: data/i386.txt tiled to {args.gib:g} GiB per GPU, needle "
                             f"{args.needle!r} (absent => full scan), DynamicAvx2Searcher::new semantics",
                 "haystack_bytes_per_gpu": S, "needle_len": k, "position": k - 1,
-                "sharding": "contiguous start-position ranges + k-1 byte right halo; NCCL all_reduce(MIN) of "
-                            "the 8-byte first offset per step, overlapped with the next step's scan (async_op, "
-                            "all waited for inside the timed region)" if world > 1 else "single GPU",
+                "sharding": ("single GPU" if world == 1 else
+                             "contiguous start-position ranges + k-1 byte right halo; " +
+                             ("first offsets MIN-reduced through peer mailboxes: 8-byte NVLink stores fused into the "
+                              "scan epilogue + a one-warp min kernel (no collective call)" if peer is not None else
+                              "NCCL all_reduce(MIN) of the 8-byte first offset per step, overlapped with the next "
+                              "step's scan (async_op, all waited for inside the timed region)")),
                 "l2": "haystack >> L2 (126 MB): every step streams from HBM, no flush needed",
                 "kernel_variant": {0: "auto", 1: "ldg", 2: "tma"}[args.variant],
             },

@@ -136,6 +136,28 @@ int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t 
 int ss_b200_find_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base_offset,
                                  size_t start_limit, void *workspace, uint64_t *d_result, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Sharded search with the exchange fused into the scan (multi-GPU, one process per GPU).
+ * Alternative to "ss_b200_find_in_device_async + ncclAllReduce(min)": the scan's last CTA stores this
+ * rank's result straight into every rank's mailbox (peer HBM over NVLink, CUDA IPC mappings), and a
+ * one-warp kernel enqueued behind the scan takes the minimum once all `world` results have landed.
+ *   ss_b200_mailbox_create   4 * world uint64 slots in device memory (cudaMalloc, IPC-exportable)
+ *   ss_b200_ipc_export/open  64-byte CUDA IPC handle out / mapped peer pointer in
+ *   mailboxes[world]         host array of device pointers: [rank] = own mailbox, others = opened handles
+ *   seq                      search counter, identical on all ranks, incremented per search
+ *   workspace                32 bytes, zero when enqueued
+ *   d_result                 receives min over ranks of (base_offset + first offset) or SS_B200_DEVICE_NONE
+ * All ranks must issue the same sequence of searches. */
+int ss_b200_mailbox_create(int world, void **d_mailbox);
+int ss_b200_mailbox_free(void *d_mailbox);
+int ss_b200_ipc_export(const void *dptr, uint8_t handle_out[64]);
+int ss_b200_ipc_open(const uint8_t handle[64], void **dptr_out);
+int ss_b200_ipc_close(void *dptr);
+int ss_b200_find_in_device_exchange_async(const ss_b200_searcher *s, const void *dptr, size_t len,
+                                          uint64_t base_offset, size_t start_limit, void *workspace,
+                                          void *const *mailboxes, int world, int rank, uint64_t seq,
+                                          uint64_t *d_result, void *stream);
+
 /* Many-haystack mode, stream-ordered: ONE needle against a device-resident SET of haystacks in a
  * single pass at the long-scan rate (the set is scanned as one blob; a match counts for haystack h
  * only if it lies wholly inside it).  Per haystack the result is search_in() of src/x86.rs:523.

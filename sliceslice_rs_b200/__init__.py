@@ -81,6 +81,12 @@ def lib() -> C.CDLL:
         "ss_b200_search_in_host": (i32, [vp, vp, sz, C.POINTER(C.c_uint8)]),
         "ss_b200_find_in_host": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "ss_b200_find_in_device_async": (i32, [vp, vp, sz, u64, sz, vp, vp, vp]),
+        "ss_b200_mailbox_create": (i32, [i32, pp]),
+        "ss_b200_mailbox_free": (i32, [vp]),
+        "ss_b200_ipc_export": (i32, [vp, vp]),
+        "ss_b200_ipc_open": (i32, [vp, pp]),
+        "ss_b200_ipc_close": (i32, [vp]),
+        "ss_b200_find_in_device_exchange_async": (i32, [vp, vp, sz, u64, sz, vp, vp, i32, i32, u64, vp, vp]),
         "ss_b200_search_many_async": (i32, [vp, vp, vp, sz, sz, vp, vp, vp]),
         "ss_b200_batch_create": (i32, [vp, vp, sz, vp, vp, sz, pp]),
         "ss_b200_batch_free": (None, [vp]),

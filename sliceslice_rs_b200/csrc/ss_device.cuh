@@ -14,6 +14,9 @@
 #include <stdint.h>
 
 #define SS_INLINE_NEEDLE_MAX 64
+#define SS_MAX_PEERS 16
+#define SS_MAILBOX_DEPTH 4                         // result slots per (rank) in flight, indexed by seq % 4
+#define SS_MAILBOX_EMPTY 0xFFFFFFFFFFFFFFFFull     // never a result: offsets and NONE are <= INT64_MAX
 #define SS_NONE_U64 0x7FFFFFFFFFFFFFFFull // SS_B200_DEVICE_NONE
 
 // 16-byte self-resetting per-stream workspace.  `key` holds ~(smallest local
@@ -47,6 +50,11 @@ struct ScanArgs {
     uint32_t xk;   // extra-anchor kind the kernel was instantiated with (see filter_word)
     uint32_t e4[2]; // extra anchor bytes splatted x4
     uint32_t xbs;  // xk == 3: 8 * needle offset (1..3) of the unaligned extra anchor
+    // peer exchange (n_peers == 0: off): the last CTA also stores the result into slot
+    // [seq % 4][rank] of every rank's mailbox (peer memory over NVLink), fused into the scan epilogue
+    unsigned long long *peer_slot[SS_MAX_PEERS];
+    uint32_t n_peers;
+    uint32_t pad_peers;
     // many-haystack mode (nullptr otherwise): hay is the concatenation of n_seg haystacks, haystack h
     // = bytes [seg_off[h], seg_off[h+1]) with seg_off[0] == 0; seg_flags[h] <- 1 when it contains the needle
     const unsigned long long *seg_off;
@@ -346,6 +354,10 @@ __device__ __forceinline__ void scan_finish(const ScanArgs &a)
             } else {
                 *a.out = r;
             }
+            // fused exchange: one 8-byte store per rank, straight into peer HBM (no fence needed:
+            // the slot value itself is the arrival signal, see mailbox_min_kernel)
+            for (uint32_t p = 0; p < a.n_peers; p++)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.peer_slot[p]), "l"(r) : "memory");
         }
     }
 }

@@ -80,17 +80,23 @@ class ShardedSearch:
     ``shard``: CUDA uint8 tensor holding this rank's bytes (owned + halo);
     ``start``/``owned``: from :func:`shard_bounds`."""
 
-    def __init__(self, shard, start: int, owned: int, group=None):
+    def __init__(self, shard, start: int, owned: int, group=None, exchange: str = "nccl"):
+        """``exchange``: "nccl" = 8-byte all_reduce(MIN) per search (works with any backend);
+        "peer" = fused into the scan epilogue through :class:`PeerExchange` (CUDA only)."""
         import torch
 
         self.shard, self.start, self.owned, self.group = shard, start, owned, group
-        self.workspace = torch.zeros(16, dtype=torch.uint8, device=shard.device)
+        self.workspace = torch.zeros(32, dtype=torch.uint8, device=shard.device)
         self.result = torch.full((1,), DEVICE_NONE, dtype=torch.int64, device=shard.device)
+        self.peer = PeerExchange(group) if exchange == "peer" else None
 
     def find_async(self, searcher, stream=None):
-        """Enqueue scan + MIN-allreduce on the current stream; returns the device result tensor."""
+        """Enqueue scan + exchange on the current stream; returns the device result tensor."""
         import torch.distributed as dist
 
+        if self.peer is not None:
+            return self.peer.find_async(searcher, self.shard, self.start, self.owned, self.workspace, self.result,
+                                        stream=stream)
         searcher.find_in_async(self.shard, self.result, self.workspace, base_offset=self.start,
                                start_limit=self.owned, stream=stream)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -122,6 +128,73 @@ class ShardedSearch:
 
     def search(self, searcher) -> bool:
         return self.find(searcher) is not None
+
+
+class PeerExchange:
+    """Mailboxes for the fused exchange (``ss_b200_find_in_device_exchange_async``): every rank owns
+    a small cudaMalloc buffer, exports it through CUDA IPC, and maps everybody else's.  The handles
+    travel once through ``torch.distributed`` (any backend); afterwards a sharded search needs no
+    collective call at all -- the scan kernel's epilogue writes the result into peer HBM."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _check, lib
+
+        self.group = group
+        multi = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        self.seq = 0
+        own = C.c_void_p()
+        _check(lib().ss_b200_mailbox_create(self.world, C.byref(own)))
+        self._own = own
+        handle = (C.c_uint8 * 64)()
+        _check(lib().ss_b200_ipc_export(own, handle))
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        self._opened = []
+        ptrs = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = own.value
+            else:
+                p = C.c_void_p()
+                buf = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                _check(lib().ss_b200_ipc_open(buf, C.byref(p)))
+                self._opened.append(p)
+                ptrs[r] = p.value
+        self.ptrs = ptrs
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=group)  # nobody posts before every mailbox is mapped and emptied
+
+    def find_async(self, searcher, shard, start: int, owned: int, workspace, result, stream=None):
+        import torch
+
+        from . import NPOS, _check, lib
+
+        if stream is None:
+            stream = torch.cuda.current_stream(shard.device)
+        self.seq += 1
+        _check(lib().ss_b200_find_in_device_exchange_async(
+            searcher._s, shard.data_ptr(), shard.numel(), int(start), NPOS if owned is None else int(owned),
+            workspace.data_ptr(), self.ptrs, self.world, self.rank, self.seq, result.data_ptr(), stream.cuda_stream))
+        return result
+
+    def close(self):
+        from . import lib
+
+        for p in self._opened:
+            lib().ss_b200_ipc_close(p)
+        self._opened = []
+        if self._own:
+            lib().ss_b200_mailbox_free(self._own)
+            self._own = None
 
 
 class ShardedHaystackSet:

@@ -31,12 +31,12 @@ def main():
         nd[min(1, k - 1)] = 0xFF
         needles.append(bytes(nd))
     ok = True
-    for nd in needles:
+    for nd, exchange in [(n_, e_) for n_ in needles for e_ in ("nccl", "peer")]:
         k = len(nd)
         start, owned, span = shard_bounds(total, k, world, rank)
         shard = torch.empty(span, dtype=torch.uint8, device="cuda")
         ss.fill_random(shard, start, seed)
-        sh = ShardedSearch(shard, start, owned)
+        sh = ShardedSearch(shard, start, owned, exchange=exchange)
         s = ss.DynamicB200Searcher.new(nd)
         assert sh.find(s) is None
         per = shard_bounds(total, k, world, 0)[1]
@@ -52,7 +52,13 @@ def main():
             got2 = sh.find_many([s, s])
             if got != plant or got2 != [plant, plant]:
                 ok = False
-                print(f"rank {rank}: k={k} plant={plant} got={got} got2={got2}", flush=True)
+                print(f"rank {rank}: {exchange} k={k} plant={plant} got={got} got2={got2}", flush=True)
+        # trivial outcomes go through the same exchange: empty needle => found at global offset 0
+        if sh.find(ss.DynamicB200Searcher.new(b"")) != 0:
+            ok = False
+            print(f"rank {rank}: {exchange} empty needle", flush=True)
+        if sh.peer is not None:
+            sh.peer.close()
     # many-haystack mode
     rng = random.Random(5)
     hays = [bytes(rng.randrange(97, 101) for _ in range(rng.randrange(0, 3000))) for _ in range(4000)]
