@@ -14,20 +14,27 @@
 #include "../../include/sliceslice_b200.h"
 #include "ss_host.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
 
 #define SS_PAIR_NONE 0xFFFFFFFFFFFFFFFFull
 
-struct NeedleDesc {
+struct MultiNeedle {       // one needle, sorted by class
     unsigned long long off; // byte offset into the needle blob
-    uint32_t k;             // length
-    uint32_t pos;           // second anchor index (k - 1; 0 for k <= 1)
-    uint32_t f4, l4;        // splatted anchors
-    uint32_t skip;          // 1: result decided on the host (k == 0 or k > n)
+    uint32_t k, pos;
+    uint32_t f4, l4;
+    uint32_t w;            // original needle index
+    uint32_t pad;
+};
+
+struct MultiGroup {
+    uint32_t first, count; // range in the sorted needle array
+    uint32_t cls;          // 8 = one-byte needles, else 2 * WS + (bs != 0)
     uint32_t pad;
 };
 
@@ -36,11 +43,21 @@ struct ss_b200_batch {
     unsigned long long *d_noff = nullptr;
     uint8_t *d_hblob = nullptr;
     unsigned long long *d_hoff = nullptr;
-    NeedleDesc *d_desc = nullptr;
     size_t n_needles = 0, n_hay = 0;
     std::vector<uint8_t> h_nblob;
     std::vector<unsigned long long> h_noff;
     int device = -1;
+    // built once at creation for ss_b200_batch_find_all_in: needles sorted by filter class + groups
+    MultiNeedle *d_multi = nullptr;
+    MultiGroup *d_groups = nullptr;
+    size_t n_multi = 0, n_groups = 0;
+    unsigned long long min_k = 0; // shortest non-empty needle
+    // per-call scratch, allocated on first use and kept (calls on one handle are serialised by `mu`)
+    mutable std::mutex mu;
+    mutable unsigned long long *d_best = nullptr; // n_needles first offsets
+    mutable uint32_t *d_bitmap = nullptr;          // triangular bitmap
+    mutable size_t bitmap_words = 0;
+    mutable unsigned long long *d_count = nullptr;
 };
 
 // error plumbing shared with capi.cu
@@ -150,121 +167,175 @@ __global__ void __launch_bounds__(256) triangular_kernel(const uint8_t *__restri
 }
 
 // ---- every needle over one long haystack -------------------------------------------------
-// CTA (segment s, needle group g): the segment's chunks are loaded into registers once and
-// tested against every needle of the group; CTAs are numbered segment-major so that early
-// segments run first and `best[w]` prunes later segments (the reference's early return).
+// CTA (segment s, needle group g).  The segment's chunks (and their successors) are loaded into
+// registers once and tested against every needle of the group.  Needles are sorted on the host by
+// filter class -- (second-anchor word offset, shift or no shift, one-byte needle), the same template
+// parameters as the long scan -- so a group runs one specialised loop with no per-needle dispatch; its
+// descriptors and the current per-needle best offsets are staged in shared memory once per CTA.  CTAs
+// are numbered segment-major so early segments run first and later ones are pruned by `best[w]` (the
+// reference's early return, src/lib.rs:242-244).  Candidates are verified from the register window as
+// in the long scan (verify_chunk), needle bytes coming from the L1-cached needle blob.
 #define SS_MN_THREADS 256
 #define SS_MN_U 2
 #define SS_MN_SEG_CHUNKS (SS_MN_THREADS * SS_MN_U)
+#define SS_MN_GROUP 64
 
 struct MultiArgs {
     const uint8_t *hay;
     unsigned long long n;
     unsigned long long last_chunk;
     const uint8_t *nblob;
-    const NeedleDesc *desc;
-    unsigned long long *best; // per needle, first offset (atomicMin), init all-ones
-    uint32_t n_needles;
+    const MultiNeedle *needles;
+    const MultiGroup *groups;
+    unsigned long long *best; // per original needle index: first offset (atomicMin), init all-ones
     uint32_t n_groups;
     uint32_t head;
 };
 
-template <int R>
-__device__ __forceinline__ void multi_test(const MultiArgs &m, const NeedleDesc &d, unsigned long long w,
-                                           const uint4 (&av)[SS_MN_U], unsigned long long c0,
-                                           const uint4 *__restrict__ chunks, unsigned long long end)
+// exact decode + register refinement + publish for one flagged chunk of one needle
+template <int WS, bool BSZ, bool K1>
+__device__ __noinline__ void multi_verify(const MultiArgs &m, const MultiNeedle &d, uint4 av, uint4 nx, uint4 lo,
+                                          uint4 hi, unsigned long long chunk, unsigned long long end)
 {
-    const bool k1 = d.k == 1;
-    const unsigned long long q = d.pos >> 4;
-    uint4 lo[SS_MN_U], hi[SS_MN_U];
-    uint32_t fl[SS_MN_U];
-    uint32_t any = 0;
+    FilterConsts fc;
+    fc.f4 = d.f4;
+    fc.l4 = d.l4;
+    fc.bs = 8u * (d.pos & 3u);
+    uint32_t z[4];
 #pragma unroll
-    for (int u = 0; u < SS_MN_U; u++) {
-        const unsigned long long c = c0 + (unsigned long long)u * SS_MN_THREADS + q;
-        if (q == 0)
-            lo[u] = av[u];
-        else
-            lo[u] = ldg16(chunks + (c < m.last_chunk ? c : m.last_chunk));
-        if (R > 0)
-            hi[u] = ldg16(chunks + (c + 1 < m.last_chunk ? c + 1 : m.last_chunk));
-        else
-            hi[u] = lo[u];
-        fl[u] = k1 ? chunk_flag<0, true>(av[u], lo[u], hi[u], d.f4, d.l4)
-                   : chunk_flag<R, false>(av[u], lo[u], hi[u], d.f4, d.l4);
-        any |= fl[u];
-    }
-    if (any == 0)
-        return;
+    for (int j = 0; j < 4; j++)
+        z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, j, fc));
     const uint8_t *nd = m.nblob + d.off;
+    if (!K1) {
+        uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
+        const uint32_t jmax = d.k - 1 < 16u ? d.k - 1 : 16u;
+        for (uint32_t j = 1; j <= jmax; j++) {
 #pragma unroll
-    for (int u = 0; u < SS_MN_U; u++) {
-        if (!fl[u])
-            continue;
-        const unsigned long long c = c0 + (unsigned long long)u * SS_MN_THREADS;
-        const long long p0 = (long long)(c * 16ull) - (long long)m.head;
-        const uint32_t aw[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
-        bool done = false;
+            for (int t = 0; t < 7; t++)
+                w[t] = __funnelshift_r(w[t], w[t + 1], 8);
+            w[7] >>= 8;
+            const uint32_t n4 = 0x01010101u * __ldg(nd + j);
+            uint32_t any = 0;
 #pragma unroll
-        for (int j = 0; j < 4 && !done; j++) {
-            uint32_t x = aw[j] ^ d.f4;
-            if (!k1)
-                x |= window_word<R>(lo[u], hi[u], j) ^ d.l4;
-            uint32_t z = swar_zero_exact(x);
-            while (z && !done) {
-                const int bit = __ffs((int)z) - 1;
-                z &= z - 1;
-                const long long i = p0 + 4 * j + (bit >> 3);
-                if (i < 0 || (unsigned long long)i >= end)
-                    continue;
-                bool eq = true;
-                for (uint32_t t = 1; t < d.k; t++) {
-                    if (__ldg(m.hay + i + t) != __ldg(nd + t)) {
-                        eq = false;
-                        break;
-                    }
-                }
-                if (eq) {
-                    atomicMin(&m.best[w], (unsigned long long)i);
-                    done = true;
+            for (int t = 0; t < 4; t++) {
+                z[t] &= swar_zero_exact(w[t] ^ n4);
+                any |= z[t];
+            }
+            if (!any)
+                return;
+        }
+    }
+    const long long p0 = (long long)(chunk * 16ull) - (long long)m.head;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t zz = z[j];
+        while (zz) {
+            const int bit = __ffs((int)zz) - 1;
+            zz &= zz - 1;
+            const long long i = p0 + 4 * j + (bit >> 3);
+            if (i < 0 || (unsigned long long)i >= end)
+                continue;
+            bool eq = true;
+            for (uint32_t t = 17; t < d.k; t++) { // only needles longer than the register window
+                if (__ldg(m.hay + i + t) != __ldg(nd + t)) {
+                    eq = false;
+                    break;
                 }
             }
+            if (eq) {
+                atomicMin(&m.best[d.w], (unsigned long long)i);
+                return; // ascending order within the chunk
+            }
+        }
+    }
+}
+
+template <int WS, bool BSZ, bool K1>
+__device__ __forceinline__ void multi_group_loop(const MultiArgs &m, const MultiNeedle *sd,
+                                                 const unsigned long long *sbest, uint32_t count,
+                                                 const uint4 (&av)[SS_MN_U], const uint4 (&nx)[SS_MN_U],
+                                                 unsigned long long c0, const uint4 *__restrict__ chunks,
+                                                 long long seg_first)
+{
+    for (uint32_t t = 0; t < count; t++) {
+        const MultiNeedle d = sd[t]; // shared-memory broadcast
+        if (d.k > m.n)
+            continue; // needle longer than the haystack: not found (src/x86.rs:357-359)
+        const unsigned long long end = m.n - d.k + 1;
+        if (seg_first >= (long long)end)
+            continue; // no start position of this needle in the segment
+        const unsigned long long cur = sbest[t];
+        if (cur != SS_PAIR_NONE && seg_first > (long long)cur)
+            continue; // an earlier segment already matched (CTA-uniform)
+        FilterConsts fc;
+        fc.f4 = d.f4;
+        fc.l4 = d.l4;
+        fc.bs = 8u * (d.pos & 3u);
+        const unsigned long long q = d.pos >> 4;
+        uint4 lo[SS_MN_U], hi[SS_MN_U];
+        uint32_t fl[SS_MN_U];
+        uint32_t any = 0;
+#pragma unroll
+        for (int u = 0; u < SS_MN_U; u++) {
+            if (K1 || q == 0) {
+                lo[u] = av[u];
+                hi[u] = nx[u];
+            } else { // second anchor 16 or more bytes away: rare (needles longer than 16 bytes)
+                const unsigned long long c = c0 + (unsigned long long)u * SS_MN_THREADS + q;
+                lo[u] = ldg16(chunks + (c < m.last_chunk ? c : m.last_chunk));
+                hi[u] = ldg16(chunks + (c + 1 < m.last_chunk ? c + 1 : m.last_chunk));
+            }
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                acc |= swar_zero_term(filter_word<WS, BSZ, K1, 0>(av[u], nx[u], lo[u], hi[u], j, fc));
+            fl[u] = acc & 0x80808080u;
+            any |= fl[u];
+        }
+        if (any) {
+#pragma unroll
+            for (int u = 0; u < SS_MN_U; u++)
+                if (fl[u])
+                    multi_verify<WS, BSZ, K1>(m, d, av[u], nx[u], lo[u], hi[u],
+                                              c0 + (unsigned long long)u * SS_MN_THREADS, end);
         }
     }
 }
 
 __global__ void __launch_bounds__(SS_MN_THREADS) multi_needle_kernel(const __grid_constant__ MultiArgs m)
 {
+    __shared__ MultiNeedle sd[SS_MN_GROUP];
+    __shared__ unsigned long long sbest[SS_MN_GROUP];
     const unsigned long long seg = blockIdx.x / m.n_groups;
-    const uint32_t grp = blockIdx.x % m.n_groups;
+    const MultiGroup g = m.groups[blockIdx.x % m.n_groups];
+    if (threadIdx.x < g.count) {
+        sd[threadIdx.x] = m.needles[g.first + threadIdx.x];
+        sbest[threadIdx.x] = ld_relaxed_u64(&m.best[sd[threadIdx.x].w]);
+    }
     const uint4 *chunks = reinterpret_cast<const uint4 *>(m.hay - m.head);
     const unsigned long long c0 = seg * SS_MN_SEG_CHUNKS + threadIdx.x;
-    uint4 av[SS_MN_U];
+    uint4 av[SS_MN_U], nx[SS_MN_U];
 #pragma unroll
     for (int u = 0; u < SS_MN_U; u++) {
         const unsigned long long c = c0 + (unsigned long long)u * SS_MN_THREADS;
         av[u] = ldg16(chunks + (c < m.last_chunk ? c : m.last_chunk));
+        nx[u] = ldg16(chunks + (c + 1 < m.last_chunk ? c + 1 : m.last_chunk));
     }
     const long long seg_first = (long long)(seg * SS_MN_SEG_CHUNKS * 16ull) - (long long)m.head;
-    for (uint32_t w = grp; w < m.n_needles; w += m.n_groups) {
-        const NeedleDesc d = m.desc[w];
-        if (d.skip)
-            continue;
-        const unsigned long long end = m.n - d.k + 1;
-        if (seg_first >= (long long)end)
-            continue; // no start position of this needle in the segment
-        const unsigned long long cur = ld_relaxed_u64(&m.best[w]);
-        if (cur != SS_PAIR_NONE && seg_first > (long long)cur)
-            continue; // an earlier segment already matched
-        switch (d.k == 1 ? 0 : (d.pos & 15)) {
-#define SS_CASE(R)                                                                                                   \
-    case R:                                                                                                          \
-        multi_test<R>(m, d, w, av, c0, chunks, end);                                                                 \
+    __syncthreads();
+    switch (g.cls) {
+#define SS_CASE(WS)                                                                                                  \
+    case 2 * WS:                                                                                                     \
+        multi_group_loop<WS, true, false>(m, sd, sbest, g.count, av, nx, c0, chunks, seg_first);                     \
+        break;                                                                                                       \
+    case 2 * WS + 1:                                                                                                 \
+        multi_group_loop<WS, false, false>(m, sd, sbest, g.count, av, nx, c0, chunks, seg_first);                    \
         break;
-            SS_CASE(0) SS_CASE(1) SS_CASE(2) SS_CASE(3) SS_CASE(4) SS_CASE(5) SS_CASE(6) SS_CASE(7) SS_CASE(8)
-            SS_CASE(9) SS_CASE(10) SS_CASE(11) SS_CASE(12) SS_CASE(13) SS_CASE(14) SS_CASE(15)
+        SS_CASE(0) SS_CASE(1) SS_CASE(2) SS_CASE(3)
 #undef SS_CASE
-        }
+    default:
+        multi_group_loop<0, true, true>(m, sd, sbest, g.count, av, nx, c0, chunks, seg_first);
+        break;
     }
 }
 
@@ -278,6 +349,63 @@ int upload(T **d, const void *h, size_t bytes)
 }
 
 } // namespace
+
+// Needle table of ss_b200_batch_find_all_in, built once per batch: every non-empty needle with
+// DynamicAvx2Searcher::new's position (k - 1), sorted by filter class, cut into groups of <= 64.
+static int build_multi_tables(ss_b200_batch *b)
+{
+    std::vector<MultiNeedle> nds;
+    nds.reserve(b->n_needles);
+    b->min_k = 0;
+    for (size_t w = 0; w < b->n_needles; w++) {
+        const unsigned long long k = b->h_noff[w + 1] - b->h_noff[w];
+        if (k == 0)
+            continue; // N0: found at 0, decided on the host
+        if (k > 0xFFFFFFFFull)
+            return SS_B200_E_ARG;
+        MultiNeedle d;
+        memset(&d, 0, sizeof d);
+        d.off = b->h_noff[w];
+        d.k = (uint32_t)k;
+        d.pos = (uint32_t)(k - 1);
+        d.f4 = 0x01010101u * b->h_nblob[d.off];
+        d.l4 = 0x01010101u * b->h_nblob[d.off + d.pos];
+        d.w = (uint32_t)w;
+        nds.push_back(d);
+        if (b->min_k == 0 || k < b->min_k)
+            b->min_k = k;
+    }
+    auto cls_of = [](const MultiNeedle &d) -> uint32_t {
+        if (d.k == 1)
+            return 8u;
+        const uint32_t r = d.pos & 15u;
+        return 2u * (r >> 2) + ((r & 3u) ? 1u : 0u);
+    };
+    std::stable_sort(nds.begin(), nds.end(),
+                     [&](const MultiNeedle &x, const MultiNeedle &y) { return cls_of(x) < cls_of(y); });
+    std::vector<MultiGroup> groups;
+    for (size_t i = 0; i < nds.size();) {
+        const uint32_t c = cls_of(nds[i]);
+        size_t j = i;
+        while (j < nds.size() && j - i < SS_MN_GROUP && cls_of(nds[j]) == c)
+            j++;
+        MultiGroup g;
+        g.first = (uint32_t)i;
+        g.count = (uint32_t)(j - i);
+        g.cls = c;
+        g.pad = 0;
+        groups.push_back(g);
+        i = j;
+    }
+    b->n_multi = nds.size();
+    b->n_groups = groups.size();
+    if (nds.empty())
+        return SS_B200_OK;
+    int rc = upload(&b->d_multi, nds.data(), nds.size() * sizeof(MultiNeedle));
+    if (rc == SS_B200_OK)
+        rc = upload(&b->d_groups, groups.data(), groups.size() * sizeof(MultiGroup));
+    return rc;
+}
 
 extern "C" int ss_b200_batch_create(const uint8_t *needle_blob, const uint64_t *needle_off, size_t n_needles,
                                     const uint8_t *hay_blob, const uint64_t *hay_off, size_t n_haystacks,
@@ -308,11 +436,8 @@ extern "C" int ss_b200_batch_create(const uint8_t *needle_blob, const uint64_t *
         rc = upload(&b->d_hblob, hay_blob, hb);
     if (rc == SS_B200_OK)
         rc = upload(&b->d_hoff, hay_off, (n_haystacks + 1) * sizeof(uint64_t));
-    if (rc == SS_B200_OK) {
-        cudaError_t e2 = cudaMalloc((void **)&b->d_desc, (n_needles + 1) * sizeof(NeedleDesc));
-        if (e2 != cudaSuccess)
-            rc = ss_capi_cuda_fail(e2, "cudaMalloc(desc)");
-    }
+    if (rc == SS_B200_OK)
+        rc = build_multi_tables(b);
     if (rc != SS_B200_OK) {
         ss_b200_batch_free(b);
         return rc;
@@ -329,7 +454,11 @@ extern "C" void ss_b200_batch_free(ss_b200_batch *b)
     cudaFree(b->d_noff);
     cudaFree(b->d_hblob);
     cudaFree(b->d_hoff);
-    cudaFree(b->d_desc);
+    cudaFree(b->d_multi);
+    cudaFree(b->d_groups);
+    cudaFree(b->d_best);
+    cudaFree(b->d_bitmap);
+    cudaFree(b->d_count);
     delete b;
 }
 
@@ -348,14 +477,23 @@ extern "C" int ss_b200_batch_search_pairs(const ss_b200_batch *b, const uint32_t
     int rc = ss_capi_device_info(dev);
     if (rc != SS_B200_OK)
         return rc;
-    uint32_t *d_pn = nullptr, *d_ph = nullptr, *d_bm = nullptr;
-    unsigned long long *d_off = nullptr;
+    // per-call device scratch, released on every exit path
+    struct Scratch {
+        void *p[4] = {nullptr, nullptr, nullptr, nullptr};
+        ~Scratch()
+        {
+            for (void *q : p)
+                cudaFree(q);
+        }
+    } sc;
     const size_t words = (n_pairs + 31) / 32;
-    SS_CUDA(cudaMalloc((void **)&d_pn, n_pairs * 4));
-    SS_CUDA(cudaMalloc((void **)&d_ph, n_pairs * 4));
-    SS_CUDA(cudaMalloc((void **)&d_bm, words * 4));
+    SS_CUDA(cudaMalloc(&sc.p[0], n_pairs * 4));
+    SS_CUDA(cudaMalloc(&sc.p[1], n_pairs * 4));
+    SS_CUDA(cudaMalloc(&sc.p[2], words * 4));
     if (offsets)
-        SS_CUDA(cudaMalloc((void **)&d_off, n_pairs * 8));
+        SS_CUDA(cudaMalloc(&sc.p[3], n_pairs * 8));
+    uint32_t *d_pn = (uint32_t *)sc.p[0], *d_ph = (uint32_t *)sc.p[1], *d_bm = (uint32_t *)sc.p[2];
+    unsigned long long *d_off = (unsigned long long *)sc.p[3];
     SS_CUDA(cudaMemcpy(d_pn, pair_needle, n_pairs * 4, cudaMemcpyHostToDevice));
     SS_CUDA(cudaMemcpy(d_ph, pair_hay, n_pairs * 4, cudaMemcpyHostToDevice));
     unsigned long long blocks = (n_pairs + 255) / 256;
@@ -371,10 +509,6 @@ extern "C" int ss_b200_batch_search_pairs(const ss_b200_batch *b, const uint32_t
     if (offsets)
         SS_CUDA(cudaMemcpy(offsets, d_off, n_pairs * 8, cudaMemcpyDeviceToHost));
     SS_CUDA(cudaDeviceSynchronize());
-    cudaFree(d_pn);
-    cudaFree(d_ph);
-    cudaFree(d_bm);
-    cudaFree(d_off);
     return SS_B200_OK;
 }
 
@@ -396,11 +530,19 @@ extern "C" int ss_b200_batch_search_triangular(const ss_b200_batch *b, uint32_t 
         return rc;
     const unsigned long long n_pairs = w * (w + 1) / 2;
     const size_t words = (size_t)((n_pairs + 31) / 32);
-    uint32_t *d_bm = nullptr;
-    unsigned long long *d_m = nullptr;
-    SS_CUDA(cudaMalloc((void **)&d_bm, words * 4));
-    SS_CUDA(cudaMalloc((void **)&d_m, 8));
-    SS_CUDA(cudaMemset(d_m, 0, 8));
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (b->bitmap_words < words) {
+        cudaFree(b->d_bitmap);
+        b->d_bitmap = nullptr;
+        b->bitmap_words = 0;
+        SS_CUDA(cudaMalloc((void **)&b->d_bitmap, words * 4));
+        b->bitmap_words = words;
+    }
+    if (!b->d_count)
+        SS_CUDA(cudaMalloc((void **)&b->d_count, 8));
+    uint32_t *d_bm = b->d_bitmap;
+    unsigned long long *d_m = b->d_count;
+    SS_CUDA(cudaMemsetAsync(d_m, 0, 8, 0));
     unsigned long long blocks = (n_pairs + 255) / 256;
     const unsigned long long cap = (unsigned long long)dev.sm_count * 16;
     if (blocks > cap)
@@ -416,8 +558,6 @@ extern "C" int ss_b200_batch_search_triangular(const ss_b200_batch *b, uint32_t 
     SS_CUDA(cudaMemcpy(&m, d_m, 8, cudaMemcpyDeviceToHost));
     if (matches)
         *matches = m;
-    cudaFree(d_bm);
-    cudaFree(d_m);
     return SS_B200_OK;
 }
 
@@ -439,32 +579,12 @@ extern "C" int ss_b200_batch_find_all_in(const ss_b200_batch *b, const ss_b200_h
     if (rc != SS_B200_OK)
         return rc;
 
-    // needle descriptors: DynamicAvx2Searcher::new => position = k - 1
-    std::vector<NeedleDesc> desc(nn);
-    unsigned long long max_end = 0;
-    for (size_t w = 0; w < nn; w++) {
-        NeedleDesc &d = desc[w];
-        memset(&d, 0, sizeof d);
-        d.off = b->h_noff[w];
-        const unsigned long long k = b->h_noff[w + 1] - b->h_noff[w];
-        if (k > 0xFFFFFFFFull)
-            return SS_B200_E_ARG;
-        d.k = (uint32_t)k;
-        d.skip = (k == 0 || k > n) ? 1u : 0u;
-        if (!d.skip) {
-            d.pos = (uint32_t)(k - 1);
-            d.f4 = 0x01010101u * b->h_nblob[d.off];
-            d.l4 = 0x01010101u * b->h_nblob[d.off + d.pos];
-            if (n - k + 1 > max_end)
-                max_end = n - k + 1;
-        }
-    }
     std::vector<unsigned long long> best(nn, SS_PAIR_NONE);
-    if (max_end > 0) {
-        unsigned long long *d_best = nullptr;
-        SS_CUDA(cudaMemcpy(b->d_desc, desc.data(), nn * sizeof(NeedleDesc), cudaMemcpyHostToDevice));
-        SS_CUDA(cudaMalloc((void **)&d_best, nn * 8));
-        SS_CUDA(cudaMemset(d_best, 0xFF, nn * 8));
+    if (b->n_groups > 0 && n >= b->min_k) {
+        std::lock_guard<std::mutex> lk(b->mu);
+        if (!b->d_best)
+            SS_CUDA(cudaMalloc((void **)&b->d_best, nn * 8));
+        SS_CUDA(cudaMemsetAsync(b->d_best, 0xFF, nn * 8, 0));
         MultiArgs m;
         memset(&m, 0, sizeof m);
         m.hay = hay;
@@ -472,25 +592,19 @@ extern "C" int ss_b200_batch_find_all_in(const ss_b200_batch *b, const ss_b200_h
         m.head = (uint32_t)(reinterpret_cast<uintptr_t>(hay) & 15);
         m.last_chunk = (m.head + n - 1) / 16;
         m.nblob = b->d_nblob;
-        m.desc = b->d_desc;
-        m.best = d_best;
-        m.n_needles = (uint32_t)nn;
+        m.needles = b->d_multi;
+        m.groups = b->d_groups;
+        m.best = b->d_best;
+        m.n_groups = (uint32_t)b->n_groups;
+        const unsigned long long max_end = n - b->min_k + 1;
         const unsigned long long n_chunks = (m.head + max_end + 15) / 16;
         const unsigned long long n_seg = (n_chunks + SS_MN_SEG_CHUNKS - 1) / SS_MN_SEG_CHUNKS;
-        // enough needle groups to fill the machine a few times over, at least ~32 needles each
-        unsigned long long groups = ((unsigned long long)dev.sm_count * 32 + n_seg - 1) / n_seg;
-        if (groups > (nn + 31) / 32)
-            groups = (nn + 31) / 32;
-        if (groups < 1)
-            groups = 1;
-        if (n_seg * groups > 0x7FFFFFFFull)
-            groups = 0x7FFFFFFFull / n_seg ? 0x7FFFFFFFull / n_seg : 1;
-        m.n_groups = (uint32_t)groups;
-        multi_needle_kernel<<<(unsigned)(n_seg * groups), SS_MN_THREADS>>>(m);
+        if (n_seg * b->n_groups > 0x7FFFFFFFull)
+            return SS_B200_E_ARG; // haystack x needle table too large for one launch
+        multi_needle_kernel<<<(unsigned)(n_seg * b->n_groups), SS_MN_THREADS>>>(m);
         ss_host_count_launch(1);
         SS_CUDA(cudaGetLastError());
-        SS_CUDA(cudaMemcpy(best.data(), d_best, nn * 8, cudaMemcpyDeviceToHost));
-        cudaFree(d_best);
+        SS_CUDA(cudaMemcpy(best.data(), b->d_best, nn * 8, cudaMemcpyDeviceToHost));
     }
     for (size_t w = 0; w < nn; w++) {
         const unsigned long long k = b->h_noff[w + 1] - b->h_noff[w];
