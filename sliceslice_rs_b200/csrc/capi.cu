@@ -246,7 +246,7 @@ extern "C" const void *ss_b200_haystack_device_ptr(const ss_b200_haystack *h) { 
 
 struct HostSlot {
     volatile unsigned long long value;
-    volatile unsigned long long seq;
+    volatile unsigned long long pad;
 };
 
 struct ThreadCtx {
@@ -256,7 +256,6 @@ struct ThreadCtx {
     SsWorkspace *ws = nullptr;
     HostSlot *slot = nullptr;   // pinned + mapped
     HostSlot *slot_dev = nullptr; // device view of the same memory
-    unsigned long long seq = 0;
     // host-path staging (lazily sized)
     static const int NBUF = 3;
     uint8_t *dbuf[NBUF] = {nullptr, nullptr, nullptr};
@@ -282,7 +281,7 @@ static int get_ctx(ThreadCtx **out)
         SS_CUDA(cudaMemset(c.ws, 0, sizeof(SsWorkspace)));
         SS_CUDA(cudaHostAlloc((void **)&c.slot, sizeof(HostSlot), cudaHostAllocMapped));
         c.slot->value = 0;
-        c.slot->seq = 0;
+        c.slot->pad = 0;
         SS_CUDA(cudaHostGetDevicePointer((void **)&c.slot_dev, (void *)c.slot, 0));
         SS_CUDA(cudaDeviceSynchronize());
         c.device = dev;
@@ -360,7 +359,6 @@ extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const voi
         return rc;
     a.ws = (SsWorkspace *)workspace;
     a.out = (unsigned long long *)d_result;
-    a.out_seq = nullptr;
     SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
     return SS_B200_OK;
 }
@@ -490,8 +488,7 @@ extern "C" int ss_b200_find_in_device_exchange_async(const ss_b200_searcher *s, 
             return rc;
         a.ws = (SsWorkspace *)workspace;
         a.out = (unsigned long long *)((uint8_t *)workspace + 16); // local copy of this rank's own result
-        a.out_seq = nullptr;
-        a.n_peers = (uint32_t)world;
+            a.n_peers = (uint32_t)world;
         for (int p = 0; p < world; p++)
             a.peer_slot[p] = (unsigned long long *)mailboxes[p] + row + rank;
         SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
@@ -541,7 +538,6 @@ extern "C" int ss_b200_search_many_async(const ss_b200_searcher *s, const void *
         return rc;
     a.ws = (SsWorkspace *)workspace;
     a.out = (unsigned long long *)((uint8_t *)workspace + 16); // scratch result slot, unused by callers
-    a.out_seq = nullptr;
     a.seg_off = (const unsigned long long *)d_offsets;
     a.seg_flags = d_flags;
     a.n_seg = n_haystacks;
@@ -577,23 +573,22 @@ static int find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t 
         return rc;
     a.ws = c->ws;
     a.out = (unsigned long long *)&c->slot_dev->value;
-    a.out_seq = (unsigned long long *)&c->slot_dev->seq;
-    a.seq = ++c->seq;
+    c->slot->value = SS_RESULT_PENDING;
     SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, c->stream));
-    // spin on the mapped sequence word; fall back to the stream status every so often
+    // spin on the mapped result word; fall back to the stream status every so often
     unsigned spins = 0;
-    while (c->slot->seq != a.seq) {
+    while (c->slot->value == SS_RESULT_PENDING) {
         if ((++spins & 0x3FF) == 0) {
             cudaError_t e = cudaStreamQuery(c->stream);
             if (e == cudaSuccess)
-                break; // kernel retired: the mapped writes are visible now
+                break; // kernel retired: the mapped write is visible now
             if (e != cudaErrorNotReady)
                 return cuda_fail(e, "scan kernel");
         }
     }
-    if (c->slot->seq != a.seq) {
+    if (c->slot->value == SS_RESULT_PENDING) {
         SS_CUDA(cudaStreamSynchronize(c->stream));
-        if (c->slot->seq != a.seq) {
+        if (c->slot->value == SS_RESULT_PENDING) {
             t_last_error = "scan kernel retired without publishing a result";
             return SS_B200_E_CUDA;
         }
@@ -725,8 +720,7 @@ extern "C" int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *ho
         ss_host_scan_geometry(a, chunk);
         a.ws = c->ws;
         a.out = c->chunk_results_dev + i;
-        a.out_seq = nullptr;
-        SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, c->stream));
+            SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, c->stream));
         SS_CUDA(cudaEventRecord(c->scanned[b], c->stream));
         submitted++;
     }

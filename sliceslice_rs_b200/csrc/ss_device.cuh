@@ -18,6 +18,7 @@
 #define SS_MAILBOX_DEPTH 4                         // result slots per (rank) in flight, indexed by seq % 4
 #define SS_MAILBOX_EMPTY 0xFFFFFFFFFFFFFFFFull     // never a result: offsets and NONE are <= INT64_MAX
 #define SS_NONE_U64 0x7FFFFFFFFFFFFFFFull // SS_B200_DEVICE_NONE
+#define SS_RESULT_PENDING 0xFFFFFFFFFFFFFFFFull // host-side marker of a mapped result slot before the kernel wrote it
 
 // 16-byte self-resetting per-stream workspace.  `key` holds ~(smallest local
 // offset found so far) so that ZERO means "nothing found": a zero-filled
@@ -38,8 +39,6 @@ struct ScanArgs {
     const uint8_t *needle_g;     // device copy of the needle when k > SS_INLINE_NEEDLE_MAX, else nullptr
     SsWorkspace *ws;
     unsigned long long *out;     // result slot: base + first offset, or SS_NONE_U64
-    unsigned long long *out_seq; // optional (mapped host) sequence slot written after *out
-    unsigned long long seq;
     uint32_t k;    // needle length (>= 1)
     uint32_t pos;  // second anchor index (`position`), < k
     uint32_t q;    // pos / 16
@@ -346,14 +345,9 @@ __device__ __forceinline__ void scan_finish(const ScanArgs &a)
             const unsigned long long key = atomicExch(&a.ws->key, 0ull);
             a.ws->done = 0;
             const unsigned long long r = key ? (a.base + ~key) : SS_NONE_U64;
-            if (a.out_seq) {
-                // mapped pinned host slot: value first, then the sequence number the host spins on
-                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.out), "l"(r) : "memory");
-                __threadfence_system();
-                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.out_seq), "l"(a.seq) : "memory");
-            } else {
-                *a.out = r;
-            }
+            // one 8-byte store: the slot may be device memory or a mapped pinned host word the caller
+            // spins on (it holds SS_RESULT_PENDING until this store lands; no fence or second flag needed)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.out), "l"(r) : "memory");
             // fused exchange: one 8-byte store per rank, straight into peer HBM (no fence needed:
             // the slot value itself is the arrival signal, see mailbox_min_kernel)
             for (uint32_t p = 0; p < a.n_peers; p++)

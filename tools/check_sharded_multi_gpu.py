@@ -24,7 +24,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     seed = 0x5EEDB20000000001
-    total = (256 << 20) + 12345
+    # --gib G: G GiB of start positions per rank (BASELINE config 5 is 8 GiB x 8 ranks = 64 GiB)
+    gib = float(sys.argv[sys.argv.index("--gib") + 1]) if "--gib" in sys.argv else 0.0
+    total = int(gib * (1 << 30)) * world if gib else (256 << 20) + 12345
     needles = []
     for k in (1, 4, 16, 64):
         nd = bytearray(random.Random(1000 + k).randrange(255) for _ in range(k))
@@ -41,8 +43,11 @@ def main():
         assert sh.find(s) is None
         per = shard_bounds(total, k, world, 0)[1]
         # plants: straddling the rank 0/1 boundary, at the very end, and early in the last rank
-        plants = sorted({max(0, per - k // 2 - 1) if world > 1 else 777, total - k, min(total - k, (world - 1) * per + 99)},
-                        reverse=True)
+        # SURVEY 8d config 5 plants: the last k bytes of the last rank; straddling a rank boundary (0/1 and
+        # the middle one); early in the last rank; inside rank 0 (the MIN must pick it over later ranks)
+        plants = sorted({max(0, per - k // 2 - 1) if world > 1 else 777, total - k,
+                         min(total - k, (world - 1) * per + 99),
+                         max(0, min(total - k, (world // 2) * per - k // 2)), min(total - k, 4242)}, reverse=True)
         ndt = torch.tensor(list(nd), dtype=torch.uint8, device="cuda")
         for plant in plants:  # descending: each new plant is the global leftmost
             lo, hi = max(plant, start), min(plant + k, start + span)
