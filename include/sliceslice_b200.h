@@ -88,7 +88,10 @@ size_t ss_b200_searcher_position(const ss_b200_searcher *s); /* private Searcher
 
 /* Copy `len` host bytes into HBM on the current device (owned by the handle). */
 int ss_b200_haystack_upload(const uint8_t *host, size_t len, ss_b200_haystack **out);
-/* Borrow `len` bytes already in device memory (any byte alignment). */
+/* Borrow `len` bytes already in device memory (any byte alignment).  The synchronous search calls
+ * run on a stream owned by the library: the bytes must be complete (no write still pending on another
+ * stream) when ss_b200_search_in / ss_b200_find_in is called.  ss_b200_find_in_device_async is the
+ * stream-ordered entry. */
 int ss_b200_haystack_from_device(const void *dptr, size_t len, ss_b200_haystack **out);
 void ss_b200_haystack_free(ss_b200_haystack *h);
 size_t ss_b200_haystack_len(const ss_b200_haystack *h);

@@ -231,6 +231,11 @@ class _SearcherBase:
         if isinstance(haystack, DeviceHaystack):
             _check(lib().ss_b200_find_in(self._s, haystack._h, C.byref(out)))
         elif _is_torch_tensor(haystack) and haystack.is_cuda:
+            # the synchronous C entry scans on the library's own stream: wait for whatever is still
+            # writing the tensor on torch's current stream (use find_in_async to stay stream-ordered)
+            import torch
+
+            torch.cuda.current_stream(haystack.device).synchronize()
             hs = DeviceHaystack.from_tensor(haystack)
             _check(lib().ss_b200_find_in(self._s, hs._h, C.byref(out)))
             hs.close()

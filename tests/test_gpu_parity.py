@@ -487,6 +487,20 @@ def test_sharded_haystack_set_on_one_gpu(world, sorted_words):
         assert acc.tolist() == [h.find(nd) >= 0 for h in hays]
 
 
+def test_find_in_waits_for_pending_tensor_writes(variant):
+    # find_in(tensor) scans on the library's stream: it must wait for writes still queued on torch's
+    # current stream (found by tools/fuzz_gpu.py: a large copy followed at once by a search)
+    n = 48 << 20
+    rng = np.random.default_rng(11)
+    pool = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    s = ss.DynamicB200Searcher.with_position(b"bbab", 0)
+    for rep in range(6):
+        h = rng.integers(0, 2, size=n, dtype=np.uint8) + 97
+        src = torch.from_numpy(h).cuda()
+        pool[8:8 + n] = src  # asynchronous device-to-device copy on torch's stream
+        assert s.find_in(pool[8:8 + n]) == h.tobytes().find(b"bbab")
+
+
 def test_const_handles_from_many_threads(i386, words):
     # reference searchers are Send + Sync (src/x86.rs:266-271)
     hs = ss.DeviceHaystack.upload(i386)
