@@ -156,6 +156,9 @@ class DeviceHaystack:
     def from_tensor(cls, t) -> "DeviceHaystack":
         if not t.is_cuda or t.dtype.itemsize != 1 or not t.is_contiguous():
             raise B200Error("from_tensor needs a contiguous 1-byte CUDA tensor")
+        import torch
+
+        torch.cuda.current_stream(t.device).synchronize()  # searches run on the library's own stream
         h = C.c_void_p()
         _check(lib().ss_b200_haystack_from_device(t.data_ptr(), t.numel(), C.byref(h)))
         return cls(h, keepalive=t)
@@ -231,12 +234,10 @@ class _SearcherBase:
         if isinstance(haystack, DeviceHaystack):
             _check(lib().ss_b200_find_in(self._s, haystack._h, C.byref(out)))
         elif _is_torch_tensor(haystack) and haystack.is_cuda:
-            # the synchronous C entry scans on the library's own stream: wait for whatever is still
-            # writing the tensor on torch's current stream (use find_in_async to stay stream-ordered)
-            import torch
-
-            torch.cuda.current_stream(haystack.device).synchronize()
-            hs = DeviceHaystack.from_tensor(haystack)
+            # the synchronous C entry scans on the library's own stream, so from_tensor first waits for
+            # whatever is still writing the tensor on torch's current stream (find_in_async stays
+            # stream-ordered instead)
+            hs = DeviceHaystack.from_tensor(haystack)  # waits for torch's current stream
             _check(lib().ss_b200_find_in(self._s, hs._h, C.byref(out)))
             hs.close()
         else:
