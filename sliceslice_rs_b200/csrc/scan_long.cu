@@ -85,9 +85,13 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
         variant = 1; // second anchor too far away for a staged tile; LDG path handles any distance
 
     if (variant == 2) {
-        const int tile_kib = (t.tile_kib == 16) ? 16 : 32;
+        // measured (profiles/r01_size_sweep.txt): 16 KiB x 4 stages x 3 CTAs/SM wins up to ~1 GiB (more,
+        // smaller tiles spread a short scan better), 32 KiB x 3 stages x 2 CTAs/SM wins by 3-5 % beyond
+        int tile_kib = t.tile_kib;
+        if (tile_kib != 16 && tile_kib != 32)
+            tile_kib = (scan_bytes >= (2ull << 30)) ? 32 : 16;
         const uint32_t tile = (uint32_t)tile_kib * 1024u;
-        int stages = t.stages > 0 ? t.stages : 3;
+        int stages = t.stages > 0 ? t.stages : (tile_kib == 32 ? 3 : 4);
         const uint32_t stage_stride = tile + ((halo + 127u) & ~127u);
         SsTmaFn fn = (tile_kib == 32) ? ss_table_tma_32(ws, bsz, qz, k1, xk) : ss_table_tma_16(ws, bsz, qz, k1, xk);
         size_t smem = (size_t)stages * stage_stride + (size_t)stages * 16 + (size_t)stages * 4 + 16;

@@ -338,10 +338,13 @@ __device__ __forceinline__ void scan_finish(const ScanArgs &a)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int prev = atomicAdd(&a.ws->done, 1u);
+        // acq_rel ticket: the release half orders this CTA's atomicMax updates of `key` (made visible to
+        // this thread by the barrier above) before the ticket, the acquire half lets the CTA that draws
+        // the last ticket read every other CTA's updates.  Cheaper than two sequentially consistent
+        // __threadfence()s on the critical path of short scans.
+        unsigned int prev;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&a.ws->done) : "memory");
         if (prev == gridDim.x - 1) {
-            __threadfence();
             const unsigned long long key = atomicExch(&a.ws->key, 0ull);
             a.ws->done = 0;
             const unsigned long long r = key ? (a.base + ~key) : SS_NONE_U64;
