@@ -189,6 +189,13 @@ def cpu_baseline(i386: bytes, needle: bytes, sample_gib: float):
         r = oracle.find(hay, needle, threads=cores)
         mt.append(time.perf_counter() - t0)
         assert r is None
+    # config 1: 'ipsum' over the 857 KB i386.txt itself (cache-resident), one thread
+    c1 = []
+    for _ in range(2000):
+        t0 = time.perf_counter()
+        r = oracle.find(i386, needle)
+        c1.append(time.perf_counter() - t0)
+    c1_us = statistics.median(c1) * 1e6
     # the literal configs 2 and 3 on one host thread, for the `extras` block of the GPU arm
     with open(os.path.join(ROOT, "data", "words.txt"), "rb") as f:
         words = [w for w in f.read().split(b"\n") if w]
@@ -203,6 +210,7 @@ def cpu_baseline(i386: bytes, needle: bytes, sample_gib: float):
         c3.append(time.perf_counter() - t0)
     assert int(offs.sum()) == 809985317 and m == 39105
     return {"value": round(one, 3), "unit": UNIT, "cores": 1, "kind": "port",
+            "config1_ipsum_i386_us": round(c1_us, 2), "config1_gbs_cache_resident": round(len(i386) / c1_us / 1e3, 2),
             "config2_literal_ms": round(min(c2) * 1e3, 3), "config3_short_ms": round(min(c3) * 1e3, 3),
             "sample": f"i386.txt tiled to {sample_gib:g} GiB in host DRAM, needle {needle!r} absent, "
                       f"{len(times)} full scans, median; C restatement of DynamicAvx2Searcher (gcc -O3 -mavx2)",
@@ -297,6 +305,28 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         "readme_i7_6700_ms": 35.181,
         "note": "L2-resident and early-exit: launch-latency-bound, no HBM-fraction claim",
     }
+    # config 4: the same buffer refilled with the counter-based generator (alphabet 0..254), needles
+    # of length 1/4/16/64 that contain 0xFF (absent by construction), DynamicAvx2Searcher::new positions
+    import random as _random
+
+    ss.fill_random(hay, 0, 0x5EEDB20000000001)
+    c4 = {}
+    for k in (1, 4, 16, 64):
+        nd = bytearray(_random.Random(1000 + k).randrange(255) for _ in range(k))
+        nd[min(1, k - 1)] = 0xFF
+        s = ss.DynamicB200Searcher.new(bytes(nd))
+        for _ in range(3):
+            s.find_in_async(hay, res, ws)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            s.find_in_async(hay, res, ws)
+        e1.record()
+        torch.cuda.synchronize()
+        assert int(res.item()) == ss.DEVICE_NONE
+        c4[f"k={k}"] = round(hay.numel() * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
+    out["config4_random_haystack_gbs"] = c4
+
     sw = [words[i] for i in sorted(range(len(words)), key=lambda i: (len(words[i]), i))]
     tri = ss.Batch(sw, sw)
     tbest = None
