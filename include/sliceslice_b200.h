@@ -139,6 +139,14 @@ int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t 
 int ss_b200_find_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base_offset,
                                  size_t start_limit, void *workspace, uint64_t *d_result, void *stream);
 
+/* Count mode, stream-ordered (SURVEY 8f "find-all / count"): *d_count receives the number of start
+ * positions i < start_limit with hay[i..i+k) == needle -- every occurrence, overlapping ones included
+ * (the reference stops at the first, src/lib.rs:242-244; this is the same scan without the early
+ * return).  workspace: 32 bytes of device memory, zero when enqueued.  The empty needle is
+ * SS_B200_E_ARG.  Shards add their counts (ncclSum). */
+int ss_b200_count_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len, size_t start_limit,
+                                  void *workspace, uint64_t *d_count, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* Sharded search with the exchange fused into the scan (multi-GPU, one process per GPU).
  * Alternative to "ss_b200_find_in_device_async + ncclAllReduce(min)": the scan's last CTA stores this

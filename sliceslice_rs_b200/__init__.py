@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         "ss_b200_search_in_host": (i32, [vp, vp, sz, C.POINTER(C.c_uint8)]),
         "ss_b200_find_in_host": (i32, [vp, vp, sz, C.POINTER(sz)]),
         "ss_b200_find_in_device_async": (i32, [vp, vp, sz, u64, sz, vp, vp, vp]),
+        "ss_b200_count_in_device_async": (i32, [vp, vp, sz, sz, vp, vp, vp]),
         "ss_b200_mailbox_create": (i32, [i32, pp]),
         "ss_b200_mailbox_free": (i32, [vp]),
         "ss_b200_ipc_export": (i32, [vp, vp]),
@@ -270,6 +271,18 @@ class _SearcherBase:
         lim = NPOS if start_limit is None else int(start_limit)
         _check(lib().ss_b200_find_in_device_async(self._s, hay.data_ptr(), hay.numel(), int(base_offset), lim,
                                                   workspace.data_ptr(), result.data_ptr(), sp))
+
+    def count_in_async(self, hay, count, workspace, start_limit: Optional[int] = None, stream=None) -> None:
+        """Stream-ordered count of all occurrences (overlapping included) in a CUDA uint8 tensor;
+        ``count``: 1-element int64 CUDA tensor, ``workspace``: >= 32 zero bytes of CUDA memory."""
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(hay.device)
+        sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        lim = NPOS if start_limit is None else int(start_limit)
+        _check(lib().ss_b200_count_in_device_async(self._s, hay.data_ptr(), hay.numel(), lim, workspace.data_ptr(),
+                                                   count.data_ptr(), sp))
 
     def search_many_async(self, hayset: "HaystackSet", flags=None, stream=None):
         """One pass over a device-resident set of haystacks (``ss_b200_search_many_async``):

@@ -545,6 +545,34 @@ extern "C" int ss_b200_search_many_async(const ss_b200_searcher *s, const void *
     return SS_B200_OK;
 }
 
+// Count mode: number of occurrences (overlapping ones included) of the needle in device memory.
+extern "C" int ss_b200_count_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len,
+                                             size_t start_limit, void *workspace, uint64_t *d_count, void *stream)
+{
+    if (!s || !d_count || !workspace || (len && !dptr))
+        return SS_B200_E_ARG;
+    const size_t k = s->needle.size();
+    if (k == 0 || k > 0xFFFFFFFFull)
+        return SS_B200_E_ARG; // the empty needle has no meaningful occurrence count
+    cudaStream_t st = (cudaStream_t)stream;
+    SS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (len < k || start_limit == 0)
+        return SS_B200_OK;
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    ScanArgs a;
+    rc = build_args(s, dptr, len, 0, start_limit, dev.device, a);
+    if (rc != SS_B200_OK)
+        return rc;
+    a.ws = (SsWorkspace *)workspace;
+    a.out = (unsigned long long *)((uint8_t *)workspace + 16); // scratch result slot
+    a.count = (unsigned long long *)d_count;
+    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
+    return SS_B200_OK;
+}
+
 // One synchronous scan of device memory through the thread's context.
 static int find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset)
 {

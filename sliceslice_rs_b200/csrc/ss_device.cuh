@@ -59,6 +59,8 @@ struct ScanArgs {
     const unsigned long long *seg_off;
     uint8_t *seg_flags;
     unsigned long long n_seg;
+    // count mode (nullptr otherwise): incremented once per occurrence
+    unsigned long long *count;
     uint8_t needle_inline[SS_INLINE_NEEDLE_MAX]; // first min(k, 64) needle bytes
 };
 
@@ -318,6 +320,11 @@ __device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx,
             if (i < 0 || (unsigned long long)i >= a.end)
                 continue;
             if (K1 || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
+                if (a.count) {
+                    // count mode: every occurrence (overlapping ones included), no early exit
+                    atomicAdd(a.count, 1ull);
+                    continue;
+                }
                 if (a.seg_off) {
                     // many-haystack mode: the blob is a concatenation of haystacks; a match counts for
                     // haystack h iff it lies entirely inside [seg_off[h], seg_off[h+1]).  No early exit.

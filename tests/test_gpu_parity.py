@@ -449,6 +449,37 @@ def test_sharded_logic_on_one_gpu(world, variant):
         host = oracle.fill_random(0, n, SEED_HAY)
 
 
+def _count_overlapping(h: bytes, nd: bytes) -> int:
+    c, i = 0, h.find(nd)
+    while i >= 0:
+        c += 1
+        i = h.find(nd, i + 1)
+    return c
+
+
+def test_count_mode(i386, variant):
+    # the same scan without the early return: every occurrence, overlapping ones included
+    ws = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    big = i386 * 12  # 10 MiB: long enough for the TMA ring, matches straddle the copies' seams
+    t = _dev(big)
+    for nd in (b"e", b"th", b"the", b"ing ", b"segment", b"ipsum", b"descriptor table", b"  ", b"\n\n"):
+        for pos in sorted({0, len(nd) - 1}):
+            s = ss.DynamicB200Searcher.with_position(nd, pos)
+            s.count_in_async(t, cnt, ws)
+            assert int(cnt.item()) == _count_overlapping(big, nd), nd
+            s.count_in_async(t, cnt, ws, start_limit=len(i386))  # only start positions of the first copy
+            assert int(cnt.item()) == _count_overlapping(big[: len(i386) + len(nd) - 1], nd), nd
+    a = _dev(b"a" * 100000)
+    s = ss.DynamicB200Searcher.new(b"aaaa")
+    s.count_in_async(a, cnt, ws)
+    assert int(cnt.item()) == 100000 - 3  # overlapping occurrences
+    s.count_in_async(a[:3], cnt, ws)
+    assert int(cnt.item()) == 0
+    with pytest.raises(ss.B200Error):
+        ss.DynamicB200Searcher.new(b"").count_in_async(a, cnt, ws)
+
+
 def test_many_haystack_mode_vs_oracle(sorted_words, i386, variant):
     # one needle against a device-resident SET of haystacks in one pass; per haystack == search_in()
     rng = random.Random(21)
