@@ -505,6 +505,20 @@ def main():
                "host_bytes_per_gpu": n_host, "steps": args.e2e_steps,
                "timer": "host wall clock around the synchronous C-ABI call, max over ranks",
                "call": "ss_b200_find_in_host (pinned host haystack, 64 MiB chunks, 3 staging buffers)"}
+        if world == 1:
+            # the same call on an ordinary (pageable) host buffer, what a caller's &[u8] normally is:
+            # staged through pinned buffers by the library's copy pool
+            import numpy as np
+
+            n_pg = min(n_host, 2 << 30)
+            pageable = np.empty(n_pg, np.uint8)
+            pageable[:] = host[:n_pg].numpy()
+            assert searcher.find_in(pageable) is None
+            t0 = time.perf_counter()
+            for _ in range(3):
+                searcher.find_in(pageable)
+            e2e["pageable_host_buffer_gbs"] = round(n_pg * 3 / (time.perf_counter() - t0) / 1e9, 3)
+            del pageable
         del host
 
     extras = None

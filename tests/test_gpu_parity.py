@@ -393,6 +393,21 @@ def test_host_path_chunked(monkeypatch, variant):
     assert oracle.find(host, nd) == 5
 
 
+def test_host_path_pageable_staging_pool():
+    # large pageable host slices go through the pinned staging ring filled by the copy pool
+    n = (150 << 20) + 1234  # several 32 MiB chunks
+    host = oracle.fill_random(0, n, SEED_HAY)  # plain numpy memory: pageable
+    nd = bytes([9, 0xFF, 8, 7, 6, 5, 4, 3, 2])
+    s = ss.DynamicB200Searcher.new(nd)
+    assert s.find_in(host) is None
+    for spot in (n - 9, (96 << 20) - 4, (64 << 20) - 9, (32 << 20) - 8, (32 << 20) - 9, 77):
+        host[spot:spot + 9] = np.frombuffer(nd, np.uint8)
+        assert s.find_in(host) == spot
+    pinned = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = host
+    assert s.find_in(pinned) == 77  # pinned memory takes the direct path
+
+
 def test_async_entry_base_offset_and_start_limit(variant):
     n = 3 << 20
     t = torch.empty(n, dtype=torch.uint8, device="cuda")
