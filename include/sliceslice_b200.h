@@ -114,8 +114,12 @@ int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haystack *h, uint
 int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t *offset);
 
 /* search_in(&[u8]) with a HOST slice: the literal analogue of src/x86.rs:523.
- * Streams the haystack to the device in chunks (pinned staging, copy/scan
- * overlap) and scans it there; PCIe-bound by construction. */
+ * Streams the haystack to the device in chunks (three device buffers, copy/scan
+ * overlap) and scans it there; PCIe-bound by construction.  Pinned (cudaHostAlloc /
+ * cudaHostRegister) memory is copied directly; a pageable slice of 8 MiB or more is
+ * staged through a pinned ring that a pool of memcpy worker threads fills in parallel
+ * (SS_B200_HOST_THREADS: worker count, default min(7, cores-1), 0 = let the driver
+ * stage; SS_B200_HOST_CHUNK_MIB: chunk size, default 64 pinned / 32 pageable). */
 int ss_b200_search_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, uint8_t *found);
 int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, size_t *offset);
 
