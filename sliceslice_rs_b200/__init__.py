@@ -109,8 +109,6 @@ def lib() -> C.CDLL:
     return L
 
 
-DECLARED_SYMBOLS = None  # filled lazily by tests from include/sliceslice_b200.h
-
 
 def _check(rc: int) -> None:
     if rc == OK:
