@@ -199,13 +199,15 @@ extern "C" int ss_b200_haystack_upload(const uint8_t *host, size_t len, ss_b200_
     int dev = -1;
     SS_CUDA(cudaGetDevice(&dev));
     uint8_t *d = nullptr;
-    SS_CUDA(cudaMalloc(&d, ((len + 15) & ~(size_t)15) + 16));
-    if (len) {
-        cudaError_t e = cudaMemcpy(d, host, len, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) {
-            cudaFree(d);
-            return cuda_fail(e, "cudaMemcpy(haystack)");
-        }
+    const size_t alloc = ((len + 15) & ~(size_t)15) + 16;
+    SS_CUDA(cudaMalloc(&d, alloc));
+    // the kernels read whole 16-byte chunks: give the padding behind the haystack a defined value
+    cudaError_t e = cudaMemset(d + len, 0, alloc - len);
+    if (e == cudaSuccess && len)
+        e = cudaMemcpy(d, host, len, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return cuda_fail(e, "cudaMemcpy(haystack)");
     }
     ss_b200_haystack *h = new (std::nothrow) ss_b200_haystack();
     if (!h) {
@@ -796,6 +798,7 @@ extern "C" int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *ho
                 cudaFree(c->dbuf[b]);
             c->dbuf[b] = nullptr;
             SS_CUDA(cudaMalloc(&c->dbuf[b], need));
+            SS_CUDA(cudaMemset(c->dbuf[b], 0, need)); // chunk tails are read as whole 16-byte words
             if (!c->copied[b]) {
                 SS_CUDA(cudaEventCreateWithFlags(&c->copied[b], cudaEventDisableTiming));
                 SS_CUDA(cudaEventCreateWithFlags(&c->scanned[b], cudaEventDisableTiming));
