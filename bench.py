@@ -243,8 +243,11 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "i386 long-haystack (i386.txt tiled), needle 'ipsum', CPU AVX2 reference path",
-                   "haystack_bytes": n},
+        "config": {"workload": f"i386 long-haystack: data/i386.txt tiled to {args.gib:g} GiB per GPU, needle "
+                               f"{args.needle!r} (absent => full scan), DynamicAvx2Searcher::new semantics",
+                   "haystack_bytes_per_gpu": int(args.gib * (1 << 30)), "needle_len": len(needle), "position": len(needle) - 1,
+                   "reference_path": "CPU AVX2 (C restatement of DynamicAvx2Searcher), all host threads, on a bounded "
+                                     "sample of the workload", "sample_bytes": n},
         "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
