@@ -100,6 +100,27 @@ static void test_ctor_contract()
     CHECK(!DynamicB200Searcher::new_("a").search_in(Bytes("")));
 }
 
+// src/lib.rs:35-104, :333-363: every needle carrier the reference accepts ([u8; N], [u8], Box/Rc/Arc, &N,
+// Vec<u8>) reaches the searcher as the same bytes; here: literal, std::string, string_view, vector, pointer+len
+static void test_needle_carriers()
+{
+    const std::string hay = "Lorem ipsum dolor sit amet, consectetur adipiscing elit";
+    const std::string s = "ipsum";
+    const std::vector<uint8_t> v(s.begin(), s.end());
+    const std::string_view sv(s);
+    const uint8_t raw[5] = {'i', 'p', 's', 'u', 'm'};
+    for (const Bytes &needle : {Bytes("ipsum"), Bytes(s), Bytes(sv), Bytes(v), Bytes(raw, sizeof raw)}) {
+        CHECK(needle.len == 5);
+        auto searcher = DynamicB200Searcher::new_(needle);
+        CHECK(searcher.needle() == v);
+        CHECK(searcher.find_in(Bytes(hay)) == std::optional<size_t>(6));
+    }
+    // needles with embedded NUL and high bytes keep their full length (no C-string truncation)
+    const uint8_t odd[4] = {0x00, 0xFF, 0x00, 0x80};
+    const uint8_t hay2[9] = {1, 2, 0x00, 0xFF, 0x00, 0x80, 3, 0, 0};
+    CHECK(DynamicB200Searcher::new_(Bytes(odd, 4)).find_in(Bytes(hay2, 9)) == std::optional<size_t>(2));
+}
+
 static std::string read_file(const char *path)
 {
     std::ifstream f(path, std::ios::binary);
@@ -122,6 +143,7 @@ int main(int argc, char **argv)
         fprintf(stderr, "usage: %s all <i386.txt> <words.txt>\n", argv[0]);
         return 2;
     }
+    test_needle_carriers();
     // KAT groups with the literal expected results of src/lib.rs:422-544
     for (const Kat &k : KATS) {
         CHECK(search(k.haystack, k.needle) == k.found);
