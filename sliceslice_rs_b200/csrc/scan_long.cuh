@@ -4,11 +4,13 @@
 // (reference src/lib.rs:253-287, :199-251): the haystack is cut into 16-byte
 // chunks counted from the 16-byte-aligned address at or below hay[0]; every lane
 // tests the 16 start positions of one chunk per step with the SWAR two-anchor
-// filter (ss_device.cuh), a warp ballot collapses the per-lane candidate flags,
-// and only warps that saw a candidate enter the exact decode + memcmp verify.
-// The leftmost match is kept with one atomicMax on ~offset; tiles are visited in
-// ascending order and a tile whose first position lies beyond the current best
-// is skipped (the reference's early return, src/lib.rs:242-244, made parallel).
+// filter (ss_device.cuh), a warp vote collapses the per-lane candidate flags,
+// and only warps that saw a candidate enter the exact decode + register-resident
+// verify (verify_chunk).  The leftmost match is kept with one atomicMax on
+// ~offset; tiles are visited in ascending order and a tile whose first position
+// lies beyond the current best is skipped (the reference's early return,
+// src/lib.rs:242-244, made parallel).  The same kernels also serve the count
+// mode and the many-haystack mode (different action on a verified match).
 //
 // Two data paths, same arithmetic:
 //   scan_ldg_kernel  coalesced 16-byte LDG straight from HBM/L2 (variant 1)

@@ -8,7 +8,9 @@
 //     any zero byte in x  <=>  candidate              (x - 0x01010101) & ~x & 0x80808080
 // The SWAR test is exact as an "any candidate in this word" test (false positives
 // only above a true zero byte), so no candidate is ever missed; exact per-byte
-// decode and the memcmp verify (src/lib.rs:216-244) run on the rare hit path.
+// decode and the memcmp verify (src/lib.rs:216-244) run on the hit path, out of the
+// same registers (verify_chunk).  Extra anchors may be folded into the filter where
+// candidates are frequent (filter_word, AdaptiveFilter); they never change a result.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -71,15 +73,6 @@ __device__ __forceinline__ uint4 ldg16(const uint4 *p)
     return r;
 }
 
-__device__ __forceinline__ uint4 ldg16_stream(const uint4 *p)
-{
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
 {
     unsigned long long v;
@@ -97,19 +90,8 @@ __device__ __forceinline__ uint32_t swar_zero_exact(uint32_t x)
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
 }
 
-// Word j (0..3) of the 16 bytes that start at byte R of the 32-byte window lo||hi.
-template <int R>
-__device__ __forceinline__ uint32_t window_word(const uint4 &lo, const uint4 &hi, int j)
-{
-    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    constexpr int ws = R / 4;
-    constexpr int bs = (R % 4) * 8;
-    if (bs == 0)
-        return v[ws + j];
-    return __funnelshift_r(v[ws + j], v[ws + j + 1], bs);
-}
-
-// Same with the shift split as R = 4*WS + bs/8: the word offset WS is a template parameter (register
+// Word j (0..3) of the 16 bytes that start at byte R of the 32-byte window lo||hi, with the shift
+// split as R = 4*WS + bs/8: the word offset WS is a template parameter (register
 // selection must be static), the bit shift `bs` (8, 16 or 24) is a launch-uniform runtime value, and
 // BSZ says bs == 0 (no funnel shift at all).  8 instantiations cover the 16 byte shifts.
 template <int WS, bool BSZ>
@@ -206,23 +188,6 @@ struct AdaptiveFilter {
         }
     }
 };
-
-// Two-anchor form with a compile-time byte shift (used by the batched multi-needle kernel).
-template <int R, bool K1>
-__device__ __forceinline__ uint32_t chunk_flag(const uint4 &a, const uint4 &lo, const uint4 &hi, uint32_t f4,
-                                               uint32_t l4)
-{
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-    uint32_t acc = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        uint32_t x = aw[j] ^ f4;
-        if (!K1)
-            x |= window_word<R>(lo, hi, j) ^ l4;
-        acc |= swar_zero_term(x);
-    }
-    return acc & 0x80808080u;
-}
 
 // memcmp of needle[from..k) against h[from..k) from global memory -- only reached by needles longer
 // than the 17 bytes the register window covers, after those 17 bytes already matched.
