@@ -82,3 +82,16 @@ def test_cpp_mirror_reference_test_shapes(binary):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok:" in r.stdout
+
+
+def test_swar_identities_exhaustive():
+    """All 2^32 words: the any-zero-byte test never misses or invents a candidate, and the exact mask
+    marks exactly the zero bytes.  The formulas are checked to be the ones the kernels compile."""
+    src = open(os.path.join(ROOT, "sliceslice_rs_b200", "csrc", "ss_device.cuh")).read()
+    assert "return (x - 0x01010101u) & ~x;" in src
+    assert "return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);" in src
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "test_swar")
+    subprocess.run(["gcc", "-O3", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_swar.c")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
