@@ -207,23 +207,8 @@ __device__ __noinline__ void multi_verify(const MultiArgs &m, const MultiNeedle 
         z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, j, fc));
     const uint8_t *nd = m.nblob + d.off;
     if (!K1) {
-        uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
-        const uint32_t jmax = d.k - 1 < 16u ? d.k - 1 : 16u;
-        for (uint32_t j = 1; j <= jmax; j++) {
-#pragma unroll
-            for (int t = 0; t < 7; t++)
-                w[t] = __funnelshift_r(w[t], w[t + 1], 8);
-            w[7] >>= 8;
-            const uint32_t n4 = 0x01010101u * __ldg(nd + j);
-            uint32_t any = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                z[t] &= swar_zero_exact(w[t] ^ n4);
-                any |= z[t];
-            }
-            if (!any)
-                return;
-        }
+        if (!refine_alive(av, nx, z, d.k, [&](uint32_t j) { return (uint32_t)__ldg(nd + j); }))
+            return;
     }
     const long long p0 = (long long)(chunk * 16ull) - (long long)m.head;
 #pragma unroll

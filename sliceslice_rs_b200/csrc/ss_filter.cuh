@@ -1,0 +1,118 @@
+// ss_filter.cuh -- the pure arithmetic of the scan: SWAR zero-byte tests, the two-anchor (+ extra
+// anchor) filter word, and the register-window refinement of the hit path.  No memory access, no
+// intrinsics that only exist on the device: every function is __host__ __device__, so the exact code
+// the kernels compile is also emulated and checked on the CPU (tests/cpp/test_filter_host.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SS_HD __host__ __device__ __forceinline__
+
+// (hi:lo) >> s, low 32 bits; s in 0..31
+SS_HD uint32_t ss_funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (uint32_t)(((((unsigned long long)hi) << 32) | lo) >> (s & 31u));
+#endif
+}
+
+// SWAR "some byte of x is zero" accumulator term (bit 7 of each byte, plus
+// possible false positives above a true zero byte).
+SS_HD uint32_t swar_zero_term(uint32_t x) { return (x - 0x01010101u) & ~x; }
+
+// Exact: 0x80 in every byte of x that is zero, 0 elsewhere.
+SS_HD uint32_t swar_zero_exact(uint32_t x)
+{
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+
+// Word j (0..3) of the 16 bytes that start at byte R of the 32-byte window lo||hi, with the shift
+// split as R = 4*WS + bs/8: the word offset WS is a template parameter (register
+// selection must be static), the bit shift `bs` (8, 16 or 24) is a launch-uniform runtime value, and
+// BSZ says bs == 0 (no funnel shift at all).  8 instantiations cover the 16 byte shifts.
+template <int WS, bool BSZ>
+SS_HD uint32_t window_word_rt(const uint4 &lo, const uint4 &hi, int j, uint32_t bs)
+{
+    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (BSZ)
+        return v[WS + j];
+    return ss_funnel_r(v[WS + j], v[WS + j + 1], bs);
+}
+
+// The filter word for 4 start positions (word j of a chunk):
+//   zero byte <=> hay[i] == needle[0] && hay[i+pos] == needle[pos] [&& extra anchors]
+// The first two terms are the reference's two anchors (VectorHash first/last, src/lib.rs:166-178,
+// :207-214).  Extra anchors (XK) only make the filter more selective -- fewer trips to the divergent
+// verify path on natural text; a real match always passes, so results never change:
+//   XK = 0  none
+//   XK = 1  needle[4]             word-aligned with the first stream: one LOP3 per word, no shift
+//   XK = 2  needle[4], needle[8]  two LOP3 per word
+//   XK = 3  needle[xo], xo in 1..3 (short needles): one funnel shift + one LOP3 per word
+//   av : haystack bytes [16c, 16c+16)      nx : the next 16 bytes [16c+16, 16c+32)
+//   lo : haystack bytes [16(c+q), +16)     hi : the 16 after lo (lo/hi == av/nx when q == 0)
+struct FilterConsts {
+    uint32_t f4, l4, bs; // needle[0] x4, needle[pos] x4, 8 * (pos % 4)
+    uint32_t e4[2];      // extra anchor bytes x4
+    uint32_t xbs;        // XK == 3: 8 * xo
+};
+
+template <int WS, bool BSZ, bool K1, int XK>
+SS_HD uint32_t filter_word(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi,
+                                                int j, const FilterConsts &fc)
+{
+    const uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
+    uint32_t x = w[j] ^ fc.f4;
+    if (!K1) {
+        x |= window_word_rt<WS, BSZ>(lo, hi, j, fc.bs) ^ fc.l4;
+        if (XK == 1 || XK == 2)
+            x |= w[j + 1] ^ fc.e4[0];
+        if (XK == 2)
+            x |= w[j + 2] ^ fc.e4[1];
+        if (XK == 3)
+            x |= ss_funnel_r(w[j], w[j + 1], fc.xbs) ^ fc.e4[0];
+    }
+    return x;
+}
+
+// Candidate test for the 16 start positions of one chunk: non-zero iff some position MAY pass the filter.
+template <int WS, bool BSZ, bool K1, int XK>
+SS_HD uint32_t chunk_flag_x(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi,
+                                                 const FilterConsts &fc)
+{
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        acc |= swar_zero_term(filter_word<WS, BSZ, K1, XK>(av, nx, lo, hi, j, fc));
+    return acc & 0x80808080u;
+}
+
+// Register-window refinement of the hit path.  `z` holds 0x80 in the byte of every start position of
+// the chunk that is still alive (initially: the positions that pass the exact two-anchor filter);
+// av||nx are the 32 haystack bytes from the chunk start.  Round j slides the window by one byte and
+// keeps a position alive only if hay[i + j] == needle[j], for all 16 positions at once; needle bytes
+// 1 .. min(k-1, 16) are covered (position 15 + offset 16 is the last byte of the window).  Returns
+// false as soon as nothing is alive.  `needle_at(j)` yields needle byte j.
+template <class NeedleAt>
+SS_HD bool refine_alive(const uint4 &av, const uint4 &nx, uint32_t (&z)[4], uint32_t k, NeedleAt needle_at)
+{
+    uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
+    const uint32_t jmax = k - 1 < 16u ? k - 1 : 16u;
+    for (uint32_t j = 1; j <= jmax; j++) {
+#pragma unroll
+        for (int t = 0; t < 7; t++)
+            w[t] = ss_funnel_r(w[t], w[t + 1], 8);
+        w[7] >>= 8;
+        const uint32_t n4 = 0x01010101u * needle_at(j);
+        uint32_t any = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            z[t] &= swar_zero_exact(w[t] ^ n4);
+            any |= z[t];
+        }
+        if (!any)
+            return false;
+    }
+    return true;
+}

@@ -87,11 +87,27 @@ def test_cpp_mirror_reference_test_shapes(binary):
 def test_swar_identities_exhaustive():
     """All 2^32 words: the any-zero-byte test never misses or invents a candidate, and the exact mask
     marks exactly the zero bytes.  The formulas are checked to be the ones the kernels compile."""
-    src = open(os.path.join(ROOT, "sliceslice_rs_b200", "csrc", "ss_device.cuh")).read()
+    src = open(os.path.join(ROOT, "sliceslice_rs_b200", "csrc", "ss_filter.cuh")).read()
     assert "return (x - 0x01010101u) & ~x;" in src
     assert "return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);" in src
     os.makedirs(BUILD, exist_ok=True)
     exe = os.path.join(BUILD, "test_swar")
     subprocess.run(["gcc", "-O3", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_swar.c")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+
+
+def test_kernel_arithmetic_emulated_on_cpu():
+    """tests/cpp/test_filter_host.cu: the filter / refinement code the kernels compile (ss_filter.cuh,
+    __host__ __device__) driven chunk by chunk on the CPU against a naive search -- no false negatives with
+    any extra-anchor kind, verified positions == naive positions."""
+    from sliceslice_rs_b200 import build
+
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "test_filter_host")
+    cmd = [build.nvcc(), "-std=c++17", "-O2", "--extended-lambda", "--expt-relaxed-constexpr", "-o", exe,
+           os.path.join(ROOT, "tests", "cpp", "test_filter_host.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe, "300000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
