@@ -11,8 +11,7 @@
 //
 // The short-haystack regime is dispatch-latency-bound on the CPU (~7.5 ns per search); here
 // one thread owns one pair and a warp ballot packs 32 results into one bitmap word.
-#include "../../include/sliceslice_b200.h"
-#include "ss_host.h"
+#include "capi_internal.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -59,17 +58,6 @@ struct ss_b200_batch {
     mutable size_t bitmap_words = 0;
     mutable unsigned long long *d_count = nullptr;
 };
-
-// error plumbing shared with capi.cu
-extern "C" const char *ss_b200_last_error(void);
-int ss_capi_cuda_fail(cudaError_t e, const char *what);
-int ss_capi_device_info(SsDeviceInfo &out);
-#define SS_CUDA(call)                                                                                                \
-    do {                                                                                                             \
-        cudaError_t e__ = (call);                                                                                    \
-        if (e__ != cudaSuccess)                                                                                      \
-            return ss_capi_cuda_fail(e__, #call);                                                                    \
-    } while (0)
 
 namespace {
 

@@ -7,6 +7,11 @@
 #include <stdint.h>
 
 #define SS_HD __host__ __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
+#define SS_UNROLL _Pragma("unroll")
+#else
+#define SS_UNROLL // the host pass (emulation test, host halves of .cu files) has no use for it
+#endif
 
 // (hi:lo) >> s, low 32 bits; s in 0..31
 SS_HD uint32_t ss_funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
@@ -82,7 +87,7 @@ SS_HD uint32_t chunk_flag_x(const uint4 &av, const uint4 &nx, const uint4 &lo, c
                                                  const FilterConsts &fc)
 {
     uint32_t acc = 0;
-#pragma unroll
+SS_UNROLL
     for (int j = 0; j < 4; j++)
         acc |= swar_zero_term(filter_word<WS, BSZ, K1, XK>(av, nx, lo, hi, j, fc));
     return acc & 0x80808080u;
@@ -100,13 +105,13 @@ SS_HD bool refine_alive(const uint4 &av, const uint4 &nx, uint32_t (&z)[4], uint
     uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
     const uint32_t jmax = k - 1 < 16u ? k - 1 : 16u;
     for (uint32_t j = 1; j <= jmax; j++) {
-#pragma unroll
+SS_UNROLL
         for (int t = 0; t < 7; t++)
             w[t] = ss_funnel_r(w[t], w[t + 1], 8);
         w[7] >>= 8;
         const uint32_t n4 = 0x01010101u * needle_at(j);
         uint32_t any = 0;
-#pragma unroll
+SS_UNROLL
         for (int t = 0; t < 4; t++) {
             z[t] &= swar_zero_exact(w[t] ^ n4);
             any |= z[t];
