@@ -78,6 +78,19 @@ def peak_hbm():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def committed_read_peak():
+    """Read-only stream ceiling measured with tools/read_peak.cu (profiles/r01_read_peak.txt)."""
+    try:
+        best = 0.0
+        with open(os.path.join(ROOT, "profiles", "r01_read_peak.txt")) as f:
+            for line in f:
+                if line.startswith("read-only stream") and line.rstrip().endswith("GB/s"):
+                    best = max(best, float(line.split(":")[1].split()[0]))
+        return best or None
+    except Exception:
+        return None
+
+
 def committed_traffic():
     """DRAM bytes per launch of the scan kernel from the committed ncu --set full capture."""
     try:
@@ -557,6 +570,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": UNIT,
                          "frac": round(achieved / peak, 4), "peak_source": peak_src,
                          "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                         "read_only_stream_gbs": committed_read_peak(),
+                         "frac_of_read_only_stream": (round(achieved / committed_read_peak(), 4)
+                                                      if committed_read_peak() else None),
                          "kernel_ms": round(kern_avg_ms, 5), "algorithmic_bytes_per_launch": kern_bytes,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "traffic_source": (traffic or {}).get("source")},
