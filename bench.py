@@ -489,8 +489,7 @@ def main():
     traffic = committed_traffic()
 
     # ---- e2e: host buffer -> C ABI -> result, copies inside the timed region ----------------
-    e2e = None
-    if not args.no_e2e:
+    def measure_e2e():
         eg = args.e2e_gib or args.gib
         n_host = min(int(eg * (1 << 30)), span)
         try:
@@ -515,7 +514,7 @@ def main():
         dt = float(td[0])
         chunk = int(os.environ.get("SS_B200_HOST_CHUNK_MIB", "64")) << 20
         n_chunks = max(1, -(-(n_host - k + 1) // chunk))
-        e2e = {"value": round(n_host * world * args.e2e_steps / dt / 1e9, 3), "unit": UNIT,
+        e2e_line = {"value": round(n_host * world * args.e2e_steps / dt / 1e9, 3), "unit": UNIT,
                "h2d_bytes_per_step": (n_host + (n_chunks - 1) * (k - 1)) * world,
                "d2h_bytes_per_step": 8 * n_chunks * world,
                "host_bytes_per_gpu": n_host, "steps": args.e2e_steps,
@@ -533,18 +532,33 @@ def main():
             t0 = time.perf_counter()
             for _ in range(3):
                 searcher.find_in(pageable)
-            e2e["pageable_host_buffer_gbs"] = round(n_pg * 3 / (time.perf_counter() - t0) / 1e9, 3)
+            e2e_line["pageable_host_buffer_gbs"] = round(n_pg * 3 / (time.perf_counter() - t0) / 1e9, 3)
             del pageable
         del host
+        return e2e_line
 
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = measure_e2e()
+        except Exception as e:  # noqa: BLE001
+            e2e = {"error": f"{type(e).__name__}: {e}"}
+
+    # context blocks: a failure here must not cost the headline line its numbers
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = extras_single_gpu(ss, torch, i386, shard, args)
+        try:
+            extras = extras_single_gpu(ss, torch, i386, shard, args)
+        except Exception as e:  # noqa: BLE001
+            extras = {"error": f"{type(e).__name__}: {e}"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         del shard
         torch.cuda.empty_cache()
-        cpu = cpu_baseline(i386, needle, args.cpu_sample_gib)
+        try:
+            cpu = cpu_baseline(i386, needle, args.cpu_sample_gib)
+        except Exception as e:  # noqa: BLE001
+            cpu = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
