@@ -292,6 +292,30 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         sweep[repr(nd.encode("latin-1"))] = round(hay.numel() * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)
     out["absent_needle_sweep_gbs"] = sweep
 
+    # second anchor chosen from a sampled histogram of the haystack (16 MiB in 4 KiB granules)
+    d_hist = torch.zeros(256, dtype=torch.int64, device="cuda")
+    ss._check(ss.lib().ss_b200_byte_histogram_device_async(hay.data_ptr(), hay.numel(), 16 << 20, d_hist.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream))
+    hist = d_hist.cpu().numpy().astype("uint64")
+    rare = {}
+    for nd in (b"consecteturadipi", b"the quick brown fox jumps ov"):
+        row = {}
+        for label, s in (("new", ss.DynamicB200Searcher.new(nd)),
+                         ("rarest", ss.DynamicB200Searcher.with_rarest_position(nd, hist))):
+            for _ in range(2):
+                s.find_in_async(hay, res, ws)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                s.find_in_async(hay, res, ws)
+            e1.record()
+            torch.cuda.synchronize()
+            assert int(res.item()) == ss.DEVICE_NONE
+            row[label] = {"position": s.position,
+                          "gbs": round(hay.numel() * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)}
+        rare[repr(nd)] = row
+    out["rarest_position_gbs"] = rare
+
     with open(os.path.join(ROOT, "data", "words.txt"), "rb") as f:
         words = [w for w in f.read().split(b"\n") if w]
     hs = ss.DeviceHaystack.upload(i386)
@@ -313,7 +337,22 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         if it:
             bbest = dt if bbest is None else min(bbest, dt)
     assert int(o2.sum()) == 809985317
+    # the same workload end to end from HOST buffers: haystack upload, needle table upload, one launch,
+    # offsets back on the host -- everything a caller holding host memory pays
+    ebest = None
+    for it in range(4):
+        t0 = time.perf_counter()
+        hs2 = ss.DeviceHaystack.upload(i386)
+        b2 = ss.Batch(words, [])
+        o3 = b2.find_all_in(hs2)
+        dt = time.perf_counter() - t0
+        b2.close()
+        hs2.close()
+        if it:
+            ebest = dt if ebest is None else min(ebest, dt)
+    assert int(o3.sum()) == 809985317
     out["config2_literal"] = {
+        "e2e_host_buffers_ms_per_iteration": round(ebest * 1e3, 3),
         "what": "all 4585 words.txt needles over the 857425-byte i386.txt, device-resident, host wall clock",
         "api_faithful_ms_per_iteration": round(best * 1e3, 3),
         "batched_single_launch_ms_per_iteration": round(bbest * 1e3, 3),

@@ -79,6 +79,17 @@ int ss_b200_searcher_new_strict(const uint8_t *needle, size_t len, ss_b200_searc
 int ss_b200_searcher_with_position_strict(const uint8_t *needle, size_t len, size_t position,
                                           ss_b200_searcher **out);
 
+/* Second-anchor selection.  The reference leaves `position` to the caller
+ * (with_position, src/x86.rs:289-297, :461-468; rationale :252-255) and its result never depends on
+ * it (src/lib.rs:375-378): only the candidate rate does.  ss_b200_rarest_position picks the index
+ * p in [1, min(len - 1, 2032)] whose byte needle[p] is rarest under `hist` (256 counts, e.g. from
+ * ss_b200_haystack_byte_histogram; NULL = a built-in text/binary background table); a position of 16 or
+ * more is charged 17/16 (the staged scan reads two more vectors per chunk then); equal costs go to the
+ * larger index, so a needle of equally frequent bytes keeps the reference's default len - 1.
+ * len < 2 gives 0.  ss_b200_searcher_new_rarest = with_position(needle, that index). */
+int ss_b200_rarest_position(const uint8_t *needle, size_t len, const uint64_t *hist, size_t *position);
+int ss_b200_searcher_new_rarest(const uint8_t *needle, size_t len, const uint64_t *hist, ss_b200_searcher **out);
+
 void ss_b200_searcher_free(ss_b200_searcher *s); /* Drop */
 size_t ss_b200_searcher_needle_len(const ss_b200_searcher *s);
 size_t ss_b200_searcher_position(const ss_b200_searcher *s); /* private Searcher::position, src/lib.rs:289-293 */
@@ -96,6 +107,14 @@ int ss_b200_haystack_from_device(const void *dptr, size_t len, ss_b200_haystack 
 void ss_b200_haystack_free(ss_b200_haystack *h);
 size_t ss_b200_haystack_len(const ss_b200_haystack *h);
 const void *ss_b200_haystack_device_ptr(const ss_b200_haystack *h);
+
+/* 256-bin byte histogram of device memory, for ss_b200_rarest_position.  sample_bytes == 0 (or >= len)
+ * counts every byte; otherwise about sample_bytes are counted in evenly spaced 4 KiB granules
+ * (granule g starts at byte g * floor(G / ceil(sample_bytes / 4096)) * 4096, G = ceil(len / 4096)).
+ * The async form writes 256 uint64 to device memory in stream order. */
+int ss_b200_byte_histogram_device_async(const void *dptr, size_t len, size_t sample_bytes, uint64_t *d_hist,
+                                        void *stream);
+int ss_b200_haystack_byte_histogram(const ss_b200_haystack *h, size_t sample_bytes, uint64_t hist[256]);
 
 /* ------------------------------------------------------------------------- */
 /* The hot call.                                                              */

@@ -92,6 +92,13 @@ public:
     DeviceHaystack &operator=(const DeviceHaystack &) = delete;
     ~DeviceHaystack() { ss_b200_haystack_free(h_); }
     size_t len() const { return ss_b200_haystack_len(h_); }
+    // 256 byte counts (sample_bytes = 0: every byte), the input of with_rarest_position
+    std::vector<uint64_t> byte_histogram(size_t sample_bytes = 0) const
+    {
+        std::vector<uint64_t> hist(256);
+        check(ss_b200_haystack_byte_histogram(h_, sample_bytes, hist.data()));
+        return hist;
+    }
     const void *device_ptr() const { return ss_b200_haystack_device_ptr(h_); }
     const ss_b200_haystack *raw() const { return h_; }
 
@@ -121,6 +128,15 @@ public:
         check(STRICT ? ss_b200_searcher_with_position_strict(needle.ptr, needle.len, position, &s)
                      : ss_b200_searcher_with_position(needle.ptr, needle.len, position, &s));
         return SearcherImpl(s, needle);
+    }
+    // with_position(needle, p), p = the index whose byte is rarest under `hist` (256 counts; nullptr =
+    // built-in background table) -- SURVEY 8f-3; results do not depend on it (src/lib.rs:375-378).
+    // The strict flavour panics on the empty needle like Avx2Searcher::new (src/x86.rs:285, :300).
+    static SearcherImpl with_rarest_position(Bytes needle, const uint64_t *hist = nullptr)
+    {
+        size_t position = 0;
+        check(ss_b200_rarest_position(needle.ptr, needle.len, hist, &position));
+        return with_position(needle, position);
     }
 
     SearcherImpl(SearcherImpl &&o) noexcept : s_(std::exchange(o.s_, nullptr)), needle_(std::move(o.needle_)) {}

@@ -29,6 +29,8 @@ extern "C" {
     fn ss_b200_searcher_with_position(needle: *const u8, len: usize, position: usize, out: *mut *mut RawSearcher) -> c_int;
     fn ss_b200_searcher_new_strict(needle: *const u8, len: usize, out: *mut *mut RawSearcher) -> c_int;
     fn ss_b200_searcher_with_position_strict(needle: *const u8, len: usize, position: usize, out: *mut *mut RawSearcher) -> c_int;
+    fn ss_b200_rarest_position(needle: *const u8, len: usize, hist: *const u64, position: *mut usize) -> c_int;
+    fn ss_b200_haystack_byte_histogram(h: *const RawHaystack, sample_bytes: usize, hist: *mut u64) -> c_int;
     fn ss_b200_searcher_free(s: *mut RawSearcher);
     fn ss_b200_haystack_upload(host: *const u8, len: usize, out: *mut *mut RawHaystack) -> c_int;
     fn ss_b200_haystack_from_device(dptr: *const c_void, len: usize, out: *mut *mut RawHaystack) -> c_int;
@@ -71,6 +73,12 @@ impl DeviceHaystack {
         check(ss_b200_haystack_from_device(dptr, len, &mut h));
         DeviceHaystack(h)
     }
+    /// 256 byte counts of the haystack (`sample_bytes == 0`: every byte), for `with_rarest_position`.
+    pub fn byte_histogram(&self, sample_bytes: usize) -> [u64; 256] {
+        let mut hist = [0u64; 256];
+        check(unsafe { ss_b200_haystack_byte_histogram(self.0, sample_bytes, hist.as_mut_ptr()) });
+        hist
+    }
 }
 impl Drop for DeviceHaystack {
     fn drop(&mut self) {
@@ -100,6 +108,15 @@ macro_rules! searcher {
                 let b = needle.as_ref();
                 check(unsafe { $with(b.as_ptr(), b.len(), position, &mut raw) });
                 Self { raw, needle }
+            }
+            /// `with_position` with the index whose byte is rarest under `hist` (`None`: built-in
+            /// background table).  Never changes a result (src/lib.rs:375-378), only the candidate rate.
+            pub fn with_rarest_position(needle: N, hist: Option<&[u64; 256]>) -> Self {
+                let mut position = 0usize;
+                let b = needle.as_ref();
+                let hp = hist.map_or(std::ptr::null(), |h| h.as_ptr());
+                check(unsafe { ss_b200_rarest_position(b.as_ptr(), b.len(), hp, &mut position) });
+                Self::with_position(needle, position)
             }
             pub fn needle(&self) -> &[u8] {
                 self.needle.as_ref()

@@ -29,7 +29,7 @@ import numpy as np
 
 __all__ = ["DynamicB200Searcher", "B200Searcher", "DeviceHaystack", "SearcherPanic", "B200Error", "lib",
            "NPOS", "DEVICE_NONE", "fill_random", "fill_tiled", "set_scan_variant", "set_scan_tuning",
-           "launch_count", "Batch", "set_extra_anchors", "HaystackSet"]
+           "launch_count", "Batch", "set_extra_anchors", "HaystackSet", "rarest_position"]
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libsliceslice_b200.so")
@@ -68,6 +68,10 @@ def lib() -> C.CDLL:
         "ss_b200_searcher_with_position": (i32, [vp, sz, sz, pp]),
         "ss_b200_searcher_new_strict": (i32, [vp, sz, pp]),
         "ss_b200_searcher_with_position_strict": (i32, [vp, sz, sz, pp]),
+        "ss_b200_rarest_position": (i32, [vp, sz, vp, C.POINTER(sz)]),
+        "ss_b200_searcher_new_rarest": (i32, [vp, sz, vp, pp]),
+        "ss_b200_byte_histogram_device_async": (i32, [vp, sz, sz, vp, vp]),
+        "ss_b200_haystack_byte_histogram": (i32, [vp, sz, vp]),
         "ss_b200_searcher_free": (None, [vp]),
         "ss_b200_searcher_needle_len": (sz, [vp]),
         "ss_b200_searcher_position": (sz, [vp]),
@@ -171,6 +175,13 @@ class DeviceHaystack:
     def __len__(self) -> int:
         return lib().ss_b200_haystack_len(self._h)
 
+    def byte_histogram(self, sample_bytes: int = 0) -> np.ndarray:
+        """256 byte counts of the haystack (``sample_bytes`` = 0: every byte; else an evenly spaced
+        sample of about that many bytes) -- the input of ``with_rarest_position``."""
+        hist = np.zeros(256, np.uint64)
+        _check(lib().ss_b200_haystack_byte_histogram(self._h, sample_bytes, hist.ctypes.data))
+        return hist
+
     @property
     def device_ptr(self) -> int:
         return lib().ss_b200_haystack_device_ptr(self._h) or 0
@@ -216,6 +227,13 @@ class _SearcherBase:
         fn = lib().ss_b200_searcher_with_position_strict if cls._STRICT else lib().ss_b200_searcher_with_position
         _check(fn(addr, n, position, C.byref(h)))
         return cls(h, nb)
+
+    @classmethod
+    def with_rarest_position(cls, needle, hist=None):
+        """``with_position(needle, p)`` with p chosen by ``rarest_position``: the index
+        whose byte is rarest under ``hist`` (256 counts, e.g. ``DeviceHaystack.byte_histogram()``;
+        None = built-in background table).  Same results as any other position (src/lib.rs:375-378)."""
+        return cls.with_position(needle, rarest_position(needle, hist))
 
     # -- accessors (the reference's private Searcher trait, src/lib.rs:289-293) ---------------
     @property
@@ -380,6 +398,21 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+def rarest_position(needle, hist=None) -> int:
+    """Second-anchor index ``ss_b200_rarest_position`` picks for ``needle`` (0 for len < 2)."""
+    nb = bytes(needle)
+    addr, n, keep = _host_view(nb)
+    hp = None
+    if hist is not None:
+        hist = np.ascontiguousarray(hist, np.uint64)
+        if hist.size != 256:
+            raise B200Error("hist must hold 256 counts")
+        hp = hist.ctypes.data
+    out = C.c_size_t(0)
+    _check(lib().ss_b200_rarest_position(addr, n, hp, C.byref(out)))
+    return out.value
 
 
 def _csr(items):

@@ -100,3 +100,60 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+# ---- second-anchor selection: a host-side rule, testable without a device ----------
+
+def _rarest_model(needle: bytes, hist):
+    """The documented rule of ss_b200_rarest_position, restated: cost = count * (16 if p < 16 else 17),
+    minimum over p in [1, min(len - 1, 2032)], ties to the larger p."""
+    if len(needle) < 2:
+        return 0
+    best, best_cost = 1, None
+    for p in range(1, min(len(needle) - 1, 2032) + 1):
+        cost = int(hist[needle[p]]) * (16 if p < 16 else 17)
+        if best_cost is None or cost <= best_cost:
+            best, best_cost = p, cost
+    return best
+
+
+def test_rarest_position_follows_the_histogram():
+    import numpy as np
+
+    rng = np.random.default_rng(7)
+    assert ss.rarest_position(b"") == 0
+    assert ss.rarest_position(b"x") == 0
+    flat = np.ones(256, np.uint64)
+    # equally frequent bytes: the reference's default (last byte, src/x86.rs:457) while it is below 16 ...
+    assert ss.rarest_position(b"ipsum", flat) == 4
+    assert ss.rarest_position(b"0123456789abcdef", flat) == 15
+    # ... and the last index of the first 16 beyond that (positions >= 16 are charged 17/16)
+    assert ss.rarest_position(bytes(range(40)), flat) == 15
+    # a clearly rarer byte further out still wins
+    h = np.full(256, 1000, np.uint64)
+    h[ord("Z")] = 3
+    assert ss.rarest_position(b"a" * 30 + b"Z" + b"a" * 10, h) == 30
+    # second anchors beyond the staged halo are never picked
+    far = b"a" * 3000 + b"Z"
+    assert ss.rarest_position(far, h) <= 2032
+    for _ in range(300):
+        k = int(rng.integers(2, 80))
+        needle = bytes(rng.integers(0, 256, k, dtype=np.uint8))
+        hist = rng.integers(0, 1 << 40, 256).astype(np.uint64)
+        assert ss.rarest_position(needle, hist) == _rarest_model(needle, hist)
+    # counts near 2^64 do not wrap the cost
+    big = np.full(256, (1 << 64) - 1, np.uint64)
+    big[7] = 5
+    assert ss.rarest_position(bytes([1, 2, 7, 3]), big) == 2
+
+
+def test_rarest_position_default_table_prefers_unusual_bytes():
+    # built-in background table: rare letters / punctuation beat common letters and the space
+    assert ss.rarest_position(b"the quiz") == 7  # 'z'
+    assert ss.rarest_position(b"e e e e#e e") == 7
+    s = ss.DynamicB200Searcher.with_rarest_position(b"consecteturadipi")
+    assert s.position == ss.rarest_position(b"consecteturadipi") and 1 <= s.position < 16
+    s.close()
+    with pytest.raises(ss.SearcherPanic):
+        ss.B200Searcher.with_rarest_position(b"")  # Avx2Searcher::new(empty) panics, src/x86.rs:285,300
+    assert ss.DynamicB200Searcher.with_rarest_position(b"").search_in(b"") is True

@@ -495,6 +495,55 @@ def test_count_mode(i386, variant):
         ss.DynamicB200Searcher.new(b"").count_in_async(a, cnt, ws)
 
 
+def _sampled_hist(data: bytes, sample_bytes: int) -> np.ndarray:
+    """CPU restatement of the documented sampling rule of ss_b200_byte_histogram_device_async."""
+    a = np.frombuffer(data, np.uint8)
+    total = (len(a) + 4095) // 4096
+    stride = 1
+    if sample_bytes and sample_bytes < len(a):
+        stride = total // ((sample_bytes + 4095) // 4096)
+    idx = np.arange(0, total, stride)
+    parts = [a[g * 4096:(g + 1) * 4096] for g in idx]
+    return np.bincount(np.concatenate(parts) if parts else a[:0], minlength=256).astype(np.uint64)
+
+
+def test_byte_histogram_and_rarest_position(i386, corpus):
+    # SURVEY 8f-3: histogram of the device-resident haystack -> rarest needle byte as second anchor
+    big = i386 * 5 + i386[:12345]
+    for data in (i386, big, i386[:4095], i386[:4097], b"a", b""):
+        for shift in (0, 1, 7):
+            t = _dev(b"\0" * shift + data)[shift:]  # unaligned device pointer
+            hs = ss.DeviceHaystack.from_tensor(t)
+            got = hs.byte_histogram()
+            assert np.array_equal(got, np.bincount(np.frombuffer(data, np.uint8), minlength=256).astype(np.uint64))
+            for sample in (4096, 100_000, 1 << 20):
+                assert np.array_equal(hs.byte_histogram(sample), _sampled_hist(data, sample)), (len(data), sample)
+            hs.close()
+    hs = ss.DeviceHaystack.upload(i386)
+    hist = hs.byte_histogram()
+    checked = 0
+    for nd in (b"consecteturadipi", b"segmentation", b"the", b" of the ", b"ipsum", b"descriptor table", b"80386",
+               b"x", b"zq", i386[70000:70300], i386[500:540]):
+        s = ss.DynamicB200Searcher.with_rarest_position(nd, hist)
+        p = s.position
+        if len(nd) >= 2:
+            # the chosen byte is the rarest one the rule may pick (positions >= 16 cost 17/16)
+            cost = lambda q: int(hist[nd[q]]) * (16 if q < 16 else 17)
+            assert 1 <= p < len(nd) and cost(p) == min(cost(q) for q in range(1, len(nd)))
+        assert s.find_in(hs) == oracle.find(i386, nd), nd  # results never depend on the position
+        s.close()
+        checked += 1
+    assert checked == 11
+    # stream-ordered form: 256 uint64 in device memory
+    d_hist = torch.zeros(256, dtype=torch.int64, device="cuda")
+    t = _dev(i386)
+    rc = ss.lib().ss_b200_byte_histogram_device_async(t.data_ptr(), t.numel(), 0, d_hist.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert np.array_equal(d_hist.cpu().numpy().astype(np.uint64), hist)
+    hs.close()
+
+
 def test_many_haystack_mode_vs_oracle(sorted_words, i386, variant):
     # one needle against a device-resident SET of haystacks in one pass; per haystack == search_in()
     rng = random.Random(21)
