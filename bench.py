@@ -250,6 +250,15 @@ def reference_arm(args):
         oracle.find(hay, needle, threads=cores)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt / 1e9
+    # the reference's own execution model is one thread per search_in (no threads in src/): time that
+    # too, on the first GiB of the sample, so the line carries both readings
+    n1 = min(n, 1 << 30)
+    one = []
+    for _ in range(3):
+        t1 = time.perf_counter()
+        assert oracle.find(hay[:n1], needle) is None
+        one.append(time.perf_counter() - t1)
+    single = n1 / min(one) / 1e9
     sample = (f"i386.txt tiled to {gib:g} GiB in host DRAM (bounded sample of the {args.gib:g} GiB/GPU workload), "
               f"needle {args.needle!r} absent, {cores} threads over contiguous slices with a k-1 halo")
     print(json.dumps({
@@ -261,7 +270,9 @@ def reference_arm(args):
                    "haystack_bytes_per_gpu": int(args.gib * (1 << 30)), "needle_len": len(needle), "position": len(needle) - 1,
                    "reference_path": "CPU AVX2 (C restatement of DynamicAvx2Searcher), all host threads, on a bounded "
                                      "sample of the workload", "sample_bytes": n},
-        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "single_thread": {"value": round(single, 3), "cores": 1,
+                                           "sample": f"first {n1 / (1 << 30):g} GiB of the same buffer, best of 3"}},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
