@@ -59,6 +59,10 @@ def parse_args():
     p.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
                    help="N > 1: how the per-shard first offsets are MIN-reduced (NCCL all_reduce, or stores into "
                         "peer mailboxes fused into the scan epilogue)")
+    p.add_argument("--mode", default="single", choices=["single", "many"],
+                   help="single = one haystack sharded by start position (the headline); many = the batched "
+                        "many-haystack mode: every GPU holds its own set of haystacks, per-haystack flags are "
+                        "OR-ed across GPUs with all_reduce(MAX)")
     p.add_argument("--no-extras", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -327,6 +331,29 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         rare[repr(nd)] = row
     out["rarest_position_gbs"] = rare
 
+    # SURVEY 8f-1 count mode: the same scan without the early return, every occurrence counted; the
+    # expected count of the 8 GiB tiling follows from the match positions of one period
+    ws32 = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    counts = {}
+    for nd in (b"ipsum", b"segment", b"the"):
+        P, m = periodic_matches(i386, nd)
+        n = hay.numel()
+        expect = int(sum((n - len(nd) - int(p)) // m + 1 for p in P if p <= n - len(nd)))
+        s = ss.DynamicB200Searcher.new(nd)
+        for _ in range(2):
+            s.count_in_async(hay, cnt, ws32)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            s.count_in_async(hay, cnt, ws32)
+        e1.record()
+        torch.cuda.synchronize()
+        assert int(cnt.item()) == expect, (nd, int(cnt.item()), expect)
+        counts[repr(nd)] = {"occurrences": expect,
+                            "gbs": round(n * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)}
+    out["count_mode_gbs"] = counts
+
     with open(os.path.join(ROOT, "data", "words.txt"), "rb") as f:
         words = [w for w in f.read().split(b"\n") if w]
     hs = ss.DeviceHaystack.upload(i386)
@@ -412,6 +439,179 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
     return out
 
 
+def periodic_matches(i386: bytes, needle: bytes):
+    """Sorted start positions in [0, m) of `needle` in the infinite tiling of i386 (m = len(i386))."""
+    import numpy as np
+
+    m, k = len(i386), len(needle)
+    ext = i386 + i386[:k - 1]
+    out, i = [], ext.find(needle)
+    while i >= 0:
+        out.append(i)
+        i = ext.find(needle, i + 1)
+    return np.asarray(out, np.int64), m
+
+
+def expected_set_flags(i386: bytes, needle: bytes, global_start: int, offsets):
+    """flags[h] = needle in tiled[global_start + offsets[h] : global_start + offsets[h+1]] for every
+    haystack of a set cut out of the i386 tiling (haystacks shorter than one period), computed from the
+    match positions of one period -- the CPU-side expectation for the full-size many-haystack run."""
+    import numpy as np
+
+    P, m = periodic_matches(i386, needle)
+    k = len(needle)
+    s = global_start + offsets[:-1].astype(np.int64)
+    e = global_start + offsets[1:].astype(np.int64)
+    if P.size == 0:
+        return np.zeros(s.size, np.uint8)
+    r = s % m
+    idx = np.searchsorted(P, r)
+    cand = np.where(idx < P.size, P[np.minimum(idx, P.size - 1)], P[0] + m)
+    return ((s - r + cand + k) <= e).astype(np.uint8)
+
+
+def many_mode(args, ss, torch, dist, world, rank, local):
+    """North-star batched mode: the haystack SET is partitioned across the GPUs (each rank holds its own
+    haystacks, needles replicated), one pass per needle at the long-scan rate, per-haystack uint8 flags
+    OR-ed over ranks with all_reduce(MAX) (NCCL has no bitwise OR).  Weak scaling: --gib per GPU."""
+    import numpy as np
+
+    i386 = load_i386()
+    needle = args.needle.encode()
+    k = len(needle)
+    S = int(args.gib * (1 << 30))
+    start = rank * S
+    # haystack lengths 0..16383 from a fixed LCG (same sequence on every rank), cut from the i386 tiling
+    rng = np.random.default_rng(20260101)
+    n_h = max(1, S // 8192 + S // 131072 + 16)  # ~6 % more than fit: the cut below always finds S
+    lens = rng.integers(0, 16384, n_h, dtype=np.int64)
+    off = np.zeros(n_h + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    cut = int(np.searchsorted(off, S, side="right")) - 1  # keep the haystacks that fit, the last takes the rest
+    off = off[:cut + 1].copy()
+    if off[-1] < S and S - off[-1] < len(i386):
+        off = np.append(off, S)
+    elif off[-1] < S:
+        off = np.append(off, off[-1] + len(i386) - 1)
+    n_h = off.size - 1
+    blob_len = int(off[-1])
+    src = torch.frombuffer(bytearray(i386), dtype=torch.uint8).cuda()
+    blob = torch.empty(blob_len, dtype=torch.uint8, device="cuda")
+    ss.fill_tiled(blob, start, src)
+    hset = ss.HaystackSet.from_device(blob, torch.from_numpy(off).cuda())
+    searcher = ss.DynamicB200Searcher.new(needle)
+    ring = [torch.zeros(n_h * world, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    pending = [None] * len(ring)
+
+    def step(i):
+        j = i % len(ring)
+        if pending[j] is not None:
+            pending[j].wait()
+            pending[j] = None
+        fl = ring[j]
+        searcher.search_many_async(hset, fl[rank * n_h:(rank + 1) * n_h])
+        if world > 1:
+            pending[j] = dist.all_reduce(fl, op=dist.ReduceOp.MAX, async_op=True)
+
+    def drain():
+        for j, w in enumerate(pending):
+            if w is not None:
+                w.wait()
+                pending[j] = None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # parity at full size, before timing: the bench needle and a present one, against the CPU expectation
+    checks = {}
+    for nd in (needle, b"segment", b"the", b"descriptor table"):
+        s2 = ss.DynamicB200Searcher.new(nd)
+        fl = ring[0]
+        fl.zero_()
+        s2.search_many_async(hset, fl[rank * n_h:(rank + 1) * n_h])
+        if world > 1:
+            dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+        got = fl.cpu().numpy()
+        exp = np.concatenate([expected_set_flags(i386, nd, r * S, off) for r in range(world)])
+        assert np.array_equal(got, exp), f"many-haystack flags differ from the CPU expectation for {nd!r}"
+        checks[repr(nd)] = int(exp.sum())
+    for f in ring:
+        f.zero_()
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step(i)
+    drain()
+    barrier()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = ss.launch_count()
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(i)
+    drain()
+    e1.record()
+    barrier()
+    launches = ss.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([e0.elapsed_time(e1), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, launches = float(mx[0]), int(sm[1])
+    else:
+        ms_total = float(tt[0])
+    assert not ring[(K - 1) % len(ring)].any().item() or checks[repr(needle)] > 0
+    # a present needle on the same set: the hit path marks haystacks instead of stopping
+    hot = {}
+    plain = ss.HaystackSet.from_device(blob, hset.offsets, prepared=False)
+    for nd in (b"segment", b"the"):
+        s2 = ss.DynamicB200Searcher.new(nd)
+        fl = ring[0][rank * n_h:(rank + 1) * n_h]
+        row = {}
+        for label, st in (("prepared_set", hset), ("no_hints", plain)):
+            for _ in range(2):
+                s2.search_many_async(st, fl)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                s2.search_many_async(st, fl)
+            b.record()
+            torch.cuda.synchronize()
+            row[label] = round(blob_len * 5 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+        hot[repr(nd)] = row
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        value = blob_len * world * K / (ms_total * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "haystack GB/s scanned (many-haystack batch)", "value": round(value, 3), "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 5),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"many-haystack batch: {n_h} haystacks per GPU (lengths 0..16383, cut from "
+                                   f"data/i386.txt tiled to {args.gib:g} GiB per GPU), needle {args.needle!r}, "
+                                   "flags[h] = search_in(haystack h)",
+                       "haystacks_per_gpu": n_h, "blob_bytes_per_gpu": blob_len,
+                       "sharding": "haystack set partitioned across GPUs; per-haystack uint8 flags OR-ed with "
+                                   "all_reduce(MAX) per step (async, all waited for inside the timed region)",
+                       "l2": "blob >> L2 (126 MB)"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": round(value / world, 2), "peak": peak, "unit": UNIT,
+                         "frac": round(value / world / peak, 4), "peak_source": peak_src,
+                         "note": "whole step (flag fill + scan + exchange) per GPU, not the kernel alone"},
+            "parity": {"flags_equal_cpu_expectation_for": checks},
+            "present_needle_gbs_per_gpu": hot,
+        }), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -439,6 +639,11 @@ def main():
     ss.set_scan_variant(args.variant)
     if args.tuning:
         ss.set_scan_tuning(*[int(x) for x in args.tuning.split(",")])
+    if args.mode == "many":
+        many_mode(args, ss, torch, dist, world, rank, local)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     i386 = load_i386()
     needle = args.needle.encode()

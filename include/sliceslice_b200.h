@@ -204,6 +204,21 @@ int ss_b200_find_in_device_exchange_async(const ss_b200_searcher *s, const void 
 int ss_b200_search_many_async(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets,
                               size_t n_haystacks, size_t blob_len, uint8_t *d_flags, void *workspace, void *stream);
 
+/* The same mode over a PREPARED set ("construct once, search many times", the reference's searcher
+ * pattern applied to the haystack side).  ss_b200_hayset_create borrows d_blob / d_offsets (they must
+ * outlive the set and stay unchanged) and builds, in stream order, one lookup hint per 4 KiB of blob --
+ * the index of the haystack holding that byte -- so that the hit path finds the haystack of a match with
+ * one or two probes instead of a binary search over the whole offset table.  Results are identical to
+ * ss_b200_search_many_async; only needles that occur in many haystacks run faster.  The search must be
+ * ordered after the create call's stream work (same stream, or an event). */
+typedef struct ss_b200_hayset ss_b200_hayset;
+int ss_b200_hayset_create(const void *d_blob, const uint64_t *d_offsets, size_t n_haystacks, size_t blob_len,
+                          void *stream, ss_b200_hayset **out);
+void ss_b200_hayset_free(ss_b200_hayset *hs);
+size_t ss_b200_hayset_len(const ss_b200_hayset *hs);
+int ss_b200_hayset_search_async(const ss_b200_searcher *s, const ss_b200_hayset *hs, uint8_t *d_flags,
+                                void *workspace, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* Batched modes (north-star "batched many-haystack mode"; workloads:
  * bench/benches/i386.rs:118-131 short sweep, :246-257 all needles over one

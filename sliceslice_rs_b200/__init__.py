@@ -93,6 +93,10 @@ def lib() -> C.CDLL:
         "ss_b200_ipc_close": (i32, [vp]),
         "ss_b200_find_in_device_exchange_async": (i32, [vp, vp, sz, u64, sz, vp, vp, i32, i32, u64, vp, vp]),
         "ss_b200_search_many_async": (i32, [vp, vp, vp, sz, sz, vp, vp, vp]),
+        "ss_b200_hayset_create": (i32, [vp, vp, sz, sz, vp, pp]),
+        "ss_b200_hayset_free": (None, [vp]),
+        "ss_b200_hayset_len": (sz, [vp]),
+        "ss_b200_hayset_search_async": (i32, [vp, vp, vp, vp, vp]),
         "ss_b200_batch_create": (i32, [vp, vp, sz, vp, vp, sz, pp]),
         "ss_b200_batch_free": (None, [vp]),
         "ss_b200_batch_search_pairs": (i32, [vp, vp, vp, sz, vp, vp]),
@@ -310,9 +314,13 @@ class _SearcherBase:
         if stream is None:
             stream = torch.cuda.current_stream(hayset.blob.device)
         sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
-        _check(lib().ss_b200_search_many_async(self._s, hayset.blob.data_ptr(), hayset.offsets.data_ptr(),
-                                               len(hayset), hayset.blob_len, flags.data_ptr(),
-                                               hayset.workspace.data_ptr(), sp))
+        if hayset.prepared:
+            _check(lib().ss_b200_hayset_search_async(self._s, hayset.handle(stream), flags.data_ptr(),
+                                                     hayset.workspace.data_ptr(), sp))
+        else:
+            _check(lib().ss_b200_search_many_async(self._s, hayset.blob.data_ptr(), hayset.offsets.data_ptr(),
+                                                   len(hayset), hayset.blob_len, flags.data_ptr(),
+                                                   hayset.workspace.data_ptr(), sp))
         return flags
 
     def close(self) -> None:
@@ -338,9 +346,13 @@ class B200Searcher(_SearcherBase):
 
 
 class HaystackSet:
-    """A set of haystacks resident in HBM as one blob + uint64 offsets (many-haystack mode)."""
+    """A set of haystacks resident in HBM as one blob + uint64 offsets (many-haystack mode).
 
-    def __init__(self, haystacks, device="cuda"):
+    ``prepared`` (default): searches go through ``ss_b200_hayset`` -- lookup hints built once on the
+    first search, so a match finds its haystack in one or two probes; ``prepared=False`` uses the
+    hint-free ``ss_b200_search_many_async``.  Same flags either way."""
+
+    def __init__(self, haystacks, device="cuda", prepared: bool = True):
         import torch
 
         blob, off = _csr(haystacks)
@@ -349,6 +361,58 @@ class HaystackSet:
         self.blob = torch.from_numpy(blob.copy()).to(device)
         self.offsets = torch.from_numpy(off.astype(np.int64)).to(device)
         self.workspace = torch.zeros(32, dtype=torch.uint8, device=device)
+        self.prepared = prepared
+        self._hs = None
+
+    def handle(self, stream=None):
+        """The ``ss_b200_hayset`` of this set, created (hints built in stream order) on first use."""
+        if self._hs is None:
+            import torch
+
+            if stream is None:
+                stream = torch.cuda.current_stream(self.blob.device)
+            sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+            h = C.c_void_p()
+            _check(lib().ss_b200_hayset_create(self.blob.data_ptr(), self.offsets.data_ptr(), self.n, self.blob_len,
+                                               sp, C.byref(h)))
+            # later searches may come in on other streams: make the hints visible to all of them
+            if hasattr(stream, "synchronize"):
+                stream.synchronize()
+            else:
+                torch.cuda.synchronize(self.blob.device)
+            self._hs = h
+        return self._hs
+
+    def close(self) -> None:
+        if self._hs:
+            lib().ss_b200_hayset_free(self._hs)
+            self._hs = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def from_device(cls, blob, offsets, prepared: bool = True) -> "HaystackSet":
+        """Wrap a set that already lives in HBM: ``blob`` = concatenated haystack bytes (CUDA uint8
+        tensor), ``offsets`` = n+1 ascending int64 byte offsets on the same device, offsets[0] == 0
+        and offsets[n] == len(blob)."""
+        import torch
+
+        if not (blob.is_cuda and offsets.is_cuda and blob.dtype == torch.uint8 and offsets.dtype == torch.int64
+                and blob.is_contiguous() and offsets.is_contiguous() and offsets.numel() >= 1):
+            raise B200Error("from_device needs a contiguous CUDA uint8 blob and CUDA int64 offsets")
+        self = cls.__new__(cls)
+        self.n = offsets.numel() - 1
+        self.blob_len = blob.numel()
+        self.blob = blob
+        self.offsets = offsets
+        self.workspace = torch.zeros(32, dtype=torch.uint8, device=blob.device)
+        self.prepared = prepared
+        self._hs = None
+        return self
 
     def __len__(self) -> int:
         return self.n

@@ -330,9 +330,9 @@ __global__ void fill_flags_kernel(uint8_t *flags, unsigned long long n, uint8_t 
         flags[i] = v;
 }
 
-extern "C" int ss_b200_search_many_async(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets,
-                                         size_t n_haystacks, size_t blob_len, uint8_t *d_flags, void *workspace,
-                                         void *stream)
+int ss_capi_search_many(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets, size_t n_haystacks,
+                        size_t blob_len, uint8_t *d_flags, void *workspace, const uint32_t *d_hint, size_t n_gran,
+                        void *stream)
 {
     if (!s || !d_offsets || !d_flags || !workspace || (blob_len && !d_blob))
         return SS_B200_E_ARG;
@@ -363,8 +363,17 @@ extern "C" int ss_b200_search_many_async(const ss_b200_searcher *s, const void *
     a.seg_off = (const unsigned long long *)d_offsets;
     a.seg_flags = d_flags;
     a.n_seg = n_haystacks;
+    a.seg_hint = d_hint;
+    a.n_gran = n_gran;
     SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
     return SS_B200_OK;
+}
+
+extern "C" int ss_b200_search_many_async(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets,
+                                         size_t n_haystacks, size_t blob_len, uint8_t *d_flags, void *workspace,
+                                         void *stream)
+{
+    return ss_capi_search_many(s, d_blob, d_offsets, n_haystacks, blob_len, d_flags, workspace, nullptr, 0, stream);
 }
 
 // Count mode: number of occurrences (overlapping ones included) of the needle in device memory.

@@ -69,3 +69,8 @@ int ss_capi_get_ctx(SsThreadCtx **out);
 // kernel arguments for one scan of (dptr, len) with this searcher (k >= 1, len >= k)
 int ss_capi_build_args(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base, size_t start_limit,
                        int dev, ScanArgs &a);
+
+// many-haystack scan shared by ss_b200_search_many_async (no hints) and ss_b200_hayset_search_async
+int ss_capi_search_many(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets, size_t n_haystacks,
+                        size_t blob_len, uint8_t *d_flags, void *workspace, const uint32_t *d_hint, size_t n_gran,
+                        void *stream);

@@ -80,7 +80,7 @@ __device__ __forceinline__ FilterConsts load_filter_consts(const ScanArgs &a)
 // Returns true when the early-exit test says this CTA can stop.
 template <int WS, bool BSZ, bool QZ, bool K1, int XK, int U, bool CLAMP>
 __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restrict__ chunks, unsigned long long cw,
-                                         int lane, const FilterConsts &fc, AdaptiveFilter &af)
+                                         int lane, const FilterConsts &fc, AdaptiveFilter &af, uint32_t &occ)
 {
     // early exit: nothing at or right of this warp's first position can beat the current best
     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
@@ -125,9 +125,12 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
             hi[u] = NEED_HI ? ldg16(pq + u * 32 + 1) : lo[u];
         }
     }
-    if (key) {
+    {
+        // every observed value of `key` is a valid bound (it only ever improves), so the warp stops as
+        // soon as any lane's reading says so; the vote keeps the decision warp-uniform whatever each
+        // lane's load returned
         const long long first_pos = (long long)(cw * 16ull) - (long long)a.head;
-        if (first_pos > (long long)~key)
+        if (__any_sync(0xFFFFFFFFu, key != 0 && first_pos > (long long)~key))
             return true;
     }
     uint32_t fl[U];
@@ -151,7 +154,7 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
         for (int u = 0; u < U; u++) {
             const unsigned long long c = c0 + u * 32;
             if (fl[u] && (!CLAMP || c < a.n_chunks))
-                verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
+                occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
         }
     }
     return false;
@@ -177,20 +180,22 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
     }
     const FilterConsts fc = load_filter_consts(a);
     AdaptiveFilter af;
+    uint32_t occ = 0; // count mode: occurrences seen by this thread
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
         bool stop;
         if (tile < n_interior) {
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af, occ);
         } else {
             if (cw >= a.n_chunks)
                 continue; // this warp's run holds no start position (warp-uniform)
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af, occ);
         }
         if (stop)
             break; // every later tile of this CTA is further right still
     }
+    count_flush(a, occ);
     scan_finish(a);
 }
 
@@ -270,6 +275,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
         // ===== consumers =====
         const FilterConsts fc = load_filter_consts(a);
         AdaptiveFilter af;
+        uint32_t occ = 0; // count mode: occurrences seen by this thread
         const uint32_t qb = a.q * 16u;
         int s = 0;
         uint32_t ph = 0;
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
                     for (int u = 0; u < U; u++) {
                         const unsigned long long c = tile_c0 + lc0 + u * 32;
                         if (fl[u] && c < a.n_chunks)
-                            verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
+                            occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
                     }
                 }
             }
@@ -339,6 +345,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
                 ph ^= 1;
             }
         }
+        count_flush(a, occ);
     }
     scan_finish(a);
 }

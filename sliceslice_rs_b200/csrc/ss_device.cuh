@@ -19,6 +19,8 @@
 #define SS_MAX_PEERS 16
 #define SS_MAILBOX_DEPTH 4                         // result slots per (rank) in flight, indexed by seq % 4
 #define SS_MAILBOX_EMPTY 0xFFFFFFFFFFFFFFFFull     // never a result: offsets and NONE are <= INT64_MAX
+#define SS_HINT_SHIFT 12                           // segment lookup hints: one per 4 KiB of blob
+#define SS_HINT_GRANULE (1ull << SS_HINT_SHIFT)
 #define SS_NONE_U64 0x7FFFFFFFFFFFFFFFull // SS_B200_DEVICE_NONE
 #define SS_RESULT_PENDING 0xFFFFFFFFFFFFFFFFull // host-side marker of a mapped result slot before the kernel wrote it
 
@@ -61,6 +63,10 @@ struct ScanArgs {
     const unsigned long long *seg_off;
     uint8_t *seg_flags;
     unsigned long long n_seg;
+    // optional lookup hints of a prepared set (ss_b200_hayset): seg_hint[g] = index of the haystack
+    // holding blob byte g * SS_HINT_GRANULE, for g < n_gran; nullptr = plain binary search
+    const uint32_t *seg_hint;
+    unsigned long long n_gran;
     // count mode (nullptr otherwise): incremented once per occurrence
     unsigned long long *count;
     uint8_t needle_inline[SS_INLINE_NEEDLE_MAX]; // first min(k, 64) needle bytes
@@ -158,6 +164,14 @@ static __device__ __noinline__ void segment_hit(const ScanArgs &a, unsigned long
 {
     // h = last segment with seg_off[h] <= i
     unsigned long long lo = 0, hi = a.n_seg; // invariant: seg_off[lo] <= i < seg_off[hi]
+    if (a.seg_hint) {
+        // the haystacks holding the first byte of this granule and of the next one bracket the answer:
+        // the 20-odd dependent probes of a search over the whole table become one or two
+        const unsigned long long g = i >> SS_HINT_SHIFT;
+        lo = __ldg(a.seg_hint + g);
+        if (g + 1 < a.n_gran)
+            hi = (unsigned long long)__ldg(a.seg_hint + g + 1) + 1;
+    }
     while (hi - lo > 1) {
         const unsigned long long mid = (lo + hi) >> 1;
         if (__ldg(a.seg_off + mid) <= i)
@@ -175,9 +189,12 @@ static __device__ __noinline__ void segment_hit(const ScanArgs &a, unsigned long
 // alive start position; each round slides the window by one byte and ANDs in the exact compare with
 // the next needle byte for all 16 positions at once.  Natural-text false candidates die in the first
 // round or two.  Survivors (17 bytes equal) of longer needles finish from global memory.
+// Returns the number of occurrences counted (count mode only; 0 in every other mode): the caller keeps
+// the running total in a register and adds it to *a.count once per warp at the end of the kernel
+// (count_flush) -- one atomic per occurrence on a single address would serialise in L2.
 template <int WS, bool BSZ, bool K1>
-__device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx, uint4 lo, uint4 hi,
-                                          unsigned long long chunk)
+__device__ __noinline__ uint32_t verify_chunk(const ScanArgs &a, uint4 av, uint4 nx, uint4 lo, uint4 hi,
+                                              unsigned long long chunk)
 {
     FilterConsts fc;
     fc.f4 = a.f4;
@@ -189,8 +206,9 @@ __device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx,
         z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, j, fc));
     if (!K1) {
         if (!refine_alive(av, nx, z, a.k, [&](uint32_t j) { return (uint32_t)a.needle_inline[j]; }))
-            return;
+            return 0;
     }
+    uint32_t occ = 0;
     const long long p0 = (long long)(chunk * 16ull) - (long long)a.head; // position of byte 0 of the chunk
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -204,7 +222,7 @@ __device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx,
             if (K1 || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
                 if (a.count) {
                     // count mode: every occurrence (overlapping ones included), no early exit
-                    atomicAdd(a.count, 1ull);
+                    occ++;
                     continue;
                 }
                 if (a.seg_off) {
@@ -215,10 +233,22 @@ __device__ __noinline__ void verify_chunk(const ScanArgs &a, uint4 av, uint4 nx,
                 }
                 atomicMax(&a.ws->key, ~(unsigned long long)i);
                 __threadfence();
-                return; // ascending order: later positions of this chunk cannot be smaller
+                return 0; // ascending order: later positions of this chunk cannot be smaller
             }
         }
     }
+    return occ;
+}
+
+// Count mode epilogue: add the warp's occurrences to *a.count with one atomic.  Called by whole,
+// converged warps before scan_finish.
+__device__ __forceinline__ void count_flush(const ScanArgs &a, uint32_t occ)
+{
+    if (a.count == nullptr)
+        return; // launch-uniform
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, occ);
+    if ((threadIdx.x & 31) == 0 && total)
+        atomicAdd(a.count, (unsigned long long)total);
 }
 
 // Grid-wide epilogue: the last CTA to finish publishes the result and restores the

@@ -94,6 +94,17 @@ static void test_ctor_contract()
     CHECK(!panics([] { DynamicB200Searcher::with_position("", 7); }));   // position ignored for N0
     CHECK(DynamicB200Searcher::new_("ipsum").position() == 4);
     CHECK(DynamicB200Searcher::with_position("ipsum", 2).position() == 2);
+    // second-anchor choice is host arithmetic: built-in table and a caller histogram
+    CHECK(DynamicB200Searcher::with_rarest_position("the quiz").position() == 7);
+    CHECK(DynamicB200Searcher::with_rarest_position("x").position() == 0);
+    CHECK(panics([] { B200Searcher::with_rarest_position(""); })); // Avx2Searcher::new(empty), src/x86.rs:285
+    {
+        std::vector<uint64_t> hist(256, 100);
+        hist['p'] = 1;
+        CHECK(DynamicB200Searcher::with_rarest_position("ipsum", hist.data()).position() == 1);
+        hist['p'] = 100; // all equal: the reference's default, the last byte (src/x86.rs:457)
+        CHECK(DynamicB200Searcher::with_rarest_position("ipsum", hist.data()).position() == 4);
+    }
     // decided on the host, no device involved
     CHECK(DynamicB200Searcher::new_("").search_in(Bytes("")));
     CHECK(!DynamicB200Searcher::new_("abcd").search_in(Bytes("abc")));
@@ -185,6 +196,16 @@ int main(int argc, char **argv)
         }
         CHECK(sum == 809985317ull);
         CHECK(!DynamicB200Searcher::new_("ipsum").search_in(hay));
+        // second anchor from the haystack's own histogram: same answers (src/lib.rs:375-378)
+        const std::vector<uint64_t> hist = hay.byte_histogram();
+        unsigned long long total = 0;
+        for (uint64_t c : hist)
+            total += c;
+        CHECK(total == i386.size());
+        for (size_t w = 0; w < words.size(); w += 97) {
+            auto s = DynamicB200Searcher::with_rarest_position(words[w], hist.data());
+            CHECK(s.find_in(hay) == find_subsequence(i386, words[w]));
+        }
     }
     // tests/i386.rs:46-56 search_short_haystack: every word in every not-shorter word; a fixed stride
     // subsample keeps the one-call-per-pair form (the full sweep runs batched in tests/test_gpu_parity.py)

@@ -549,7 +549,8 @@ def test_many_haystack_mode_vs_oracle(sorted_words, i386, variant):
     rng = random.Random(21)
     hays = list(sorted_words) + [b"", b"a", b"", i386[:70000], b"xyz" * 5000, b"", i386[300000:340000], b"q"]
     rng.shuffle(hays)
-    hs = ss.HaystackSet(hays)
+    hs = ss.HaystackSet(hays)                        # prepared: lookup hints (ss_b200_hayset)
+    hs_plain = ss.HaystackSet(hays, prepared=False)  # hint-free ss_b200_search_many_async
     needles = [b"", b"a", b"e", b"th", b"the", b"tion", b"segment", b"ipsum", b"zq", b"xyzx", b"interrupt",
                b"descriptor table", i386[1000:1040], i386[69990:70010], i386[339980:340000], b"q"]
     for nd in needles:
@@ -559,7 +560,29 @@ def test_many_haystack_mode_vs_oracle(sorted_words, i386, variant):
             exp = oracle.pairs([nd], hays, np.zeros(len(hays), np.uint32), np.arange(len(hays), dtype=np.uint32))
             assert np.array_equal(got, exp != oracle.NPOS), nd
             assert got.tolist() == [h.find(nd) >= 0 for h in hays]
+            assert np.array_equal(s.search_many_async(hs_plain).cpu().numpy().astype(bool), got), nd
             s.close()
+
+
+def test_prepared_set_hints_with_awkward_boundaries():
+    # haystack boundaries on, just before and just after the 4 KiB hint granules; runs of empty
+    # haystacks (equal offsets) at granule boundaries; one haystack spanning many granules
+    rng = random.Random(5)
+    lens = [4096, 0, 0, 4095, 1, 0, 4097, 8191, 1, 0, 0, 0, 40000, 3, 4093, 0, 12288, 5, 0]
+    lens += [rng.choice([0, 1, 2, 7, 100, 4096, 5000]) for _ in range(400)]
+    alphabet = b"ab"
+    hays = [bytes(rng.choice(alphabet) for _ in range(n)) for n in lens]
+    hs = ss.HaystackSet(hays)
+    hs_plain = ss.HaystackSet(hays, prepared=False)
+    for nd in (b"a", b"ab", b"abba", b"aaaaaaaa", b"abababababab", b"bbbbbbbbbbbbbbbbbbbb", b"b" * 40):
+        s = ss.DynamicB200Searcher.new(nd)
+        got = s.search_many_async(hs).cpu().numpy().astype(bool)
+        assert got.tolist() == [h.find(nd) >= 0 for h in hays], nd
+        assert np.array_equal(s.search_many_async(hs_plain).cpu().numpy().astype(bool), got), nd
+        s.close()
+    # an empty set and a set of empty haystacks
+    assert ss.DynamicB200Searcher.new(b"a").search_many_async(ss.HaystackSet([b"", b"", b""])).cpu().tolist() == [0, 0, 0]
+    assert ss.DynamicB200Searcher.new(b"").search_many_async(ss.HaystackSet([b"", b"x"])).cpu().tolist() == [1, 1]
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
