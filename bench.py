@@ -50,6 +50,8 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--gib", type=float, default=8.0, help="haystack GiB per GPU")
+    p.add_argument("--total-gib", type=float, default=0.0,
+                   help="strong-scaling point: total haystack GiB split evenly over the GPUs (overrides --gib)")
     p.add_argument("--needle", default="ipsum")
     p.add_argument("--variant", type=int, default=0, help="0 auto, 1 LDG, 2 TMA")
     p.add_argument("--tuning", default="", help="ctas_per_sm,unroll,tile_kib,stages")
@@ -614,6 +616,9 @@ def many_mode(args, ss, torch, dist, world, rank, local):
 
 def main():
     args = parse_args()
+    strong = args.total_gib > 0
+    if strong:
+        args.gib = args.total_gib / max(int(os.environ.get("WORLD_SIZE", "1")), 1)
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -631,6 +636,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
@@ -819,7 +825,7 @@ def main():
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / K, 5), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {
                 "workload": f"i386 long-haystack: data/i386.txt tiled to {args.gib:g} GiB per GPU, needle "
                             f"{args.needle!r} (absent => full scan), DynamicAvx2Searcher::new semantics",
@@ -843,8 +849,12 @@ def main():
                          "frac_of_read_only_stream": (round(achieved / committed_read_peak(), 4)
                                                       if committed_read_peak() else None),
                          "kernel_ms": round(kern_avg_ms, 5), "algorithmic_bytes_per_launch": kern_bytes,
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                         "traffic_source": (traffic or {}).get("source")},
+                         # the committed ncu capture is of the default 8 GiB launch: it says nothing about
+                         # launches of another size
+                         "traffic": ((traffic or {}).get("dram_bytes_per_launch")
+                                     if abs(kern_bytes - (8 << 30)) < (1 << 20) else None),
+                         "traffic_source": ((traffic or {}).get("source")
+                                            if abs(kern_bytes - (8 << 30)) < (1 << 20) else None)},
             "cpu_baseline": cpu,
             "parity": "needle absent on every step (result == DEVICE_NONE on all ranks); see tests/ -m gpu",
         }
