@@ -125,6 +125,24 @@ def search_in(hay, needle, position=None, dynamic=True):
     return find(hay, needle, position, dynamic) is not None
 
 
+def count(hay, needle):
+    """Number of occurrences (overlapping ones included): the reference's search restarted one byte
+    after every match -- what `search_in` would report if its loop did not return at the first
+    verified candidate (src/lib.rs:242-244).  Checker for the count mode."""
+    import numpy as np
+
+    a = np.frombuffer(bytes(hay), np.uint8) if not isinstance(hay, np.ndarray) else hay
+    if len(needle) == 0:
+        raise ValueError("the empty needle has no occurrence count")
+    total, start = 0, 0
+    while True:
+        r = find(a[start:], needle)
+        if r is None:
+            return total
+        total += 1
+        start += r + 1
+
+
 def count_candidates(hay, needle, position=None):
     hp, n, _h = _buf(hay)
     np_, k, _n = _buf(needle)

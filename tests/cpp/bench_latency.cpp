@@ -1,6 +1,10 @@
-// bench_latency.cpp -- per-call latency of the synchronous C-ABI entry points (development tool).
+// bench_latency.cpp -- per-call latency of the C-ABI entry points (development tool).
+//   g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include tests/cpp/bench_latency.cpp \
+//       -Lsliceslice_rs_b200 -lsliceslice_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/sliceslice_rs_b200
 //   bench_latency <i386.txt> <words.txt>
 #include "sliceslice_b200.hpp"
+
+#include <cuda_runtime.h>
 
 #include <chrono>
 #include <cstdio>
@@ -49,6 +53,36 @@ int main(int argc, char **argv)
         double ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
         printf("long sweep (one find_in per word, device haystack): %.3f ms/iteration, %.2f us/call, sum %llu\n", ms,
                ms * 1e3 / searchers.size(), sum);
+    }
+    // the same loop stream-ordered: one ss_b200_find_in_device_async per word, results in device memory,
+    // one synchronisation at the end (what an async-aware caller of the drop-in would do)
+    {
+        uint64_t *d_res = nullptr;
+        void *d_ws = nullptr;
+        cudaMalloc(&d_res, searchers.size() * sizeof(uint64_t));
+        cudaMalloc(&d_ws, 32);
+        cudaMemset(d_ws, 0, 32);
+        cudaStream_t st;
+        cudaStreamCreate(&st);
+        std::vector<uint64_t> res(searchers.size());
+        for (int it = 0; it < 4; it++) {
+            auto t0 = clk::now();
+            for (size_t w = 0; w < searchers.size(); w++)
+                searchers[w].find_in_device_async(hay.device_ptr(), hay.len(), 0, SS_B200_NPOS, d_ws, d_res + w, st);
+            const double enq_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+            cudaMemcpyAsync(res.data(), d_res, res.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            double ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+            printf("  (host enqueue alone: %.3f ms = %.2f us/call)\n", enq_ms, enq_ms * 1e3 / searchers.size());
+            sum = 0;
+            for (uint64_t v : res)
+                sum += v;
+            printf("long sweep (one find_in_device_async per word, one sync): %.3f ms/iteration, %.2f us/call, sum %llu\n",
+                   ms, ms * 1e3 / searchers.size(), sum);
+        }
+        cudaFree(d_res);
+        cudaFree(d_ws);
+        cudaStreamDestroy(st);
     }
     auto absent = DynamicB200Searcher::new_("ipsum");
     for (int it = 0; it < 3; it++) {

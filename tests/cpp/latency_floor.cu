@@ -42,5 +42,21 @@ int main()
                 printf("grid %4d x 256: %.2f us per launch + mapped-flag completion\n", grid, us);
         }
     }
+    // pipelined: launches queued back to back on one stream, one synchronisation at the end --
+    // the launch-rate floor under any stream-ordered one-kernel-per-search loop
+    for (int grid : {1, 210}) {
+        for (int rep = 0; rep < 2; rep++) {
+            const int iters = 5000;
+            cudaStreamSynchronize(st);
+            auto t0 = std::chrono::steady_clock::now();
+            for (int i = 1; i <= iters; i++)
+                signal_kernel<<<grid, 256, 0, st>>>(slot_dev, (unsigned long long)i, done);
+            double enq = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / iters;
+            cudaStreamSynchronize(st);
+            double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / iters;
+            if (rep)
+                printf("grid %4d x 256 pipelined: %.2f us per launch (host enqueue alone %.2f us)\n", grid, us, enq);
+        }
+    }
     return 0;
 }

@@ -45,3 +45,32 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_full_size_expectations_match_brute_force():
+    """bench.py checks its full-size count-mode and many-haystack results against closed-form CPU
+    expectations derived from one period of the i386 tiling; pin those formulas on small cases."""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    import oracle
+
+    with open(os.path.join(ROOT, "data", "i386.txt"), "rb") as f:
+        i386 = f.read()
+    m = len(i386)
+    rng = np.random.default_rng(3)
+    for nd in (b"segment", b"the", b"ipsum", b"descriptor table", b"e\n"):
+        P, mm = bench.periodic_matches(i386, nd)
+        assert mm == m
+        for gs in (0, 54321, 5 * m - 3):
+            lens = rng.integers(0, 16384, 120)
+            off = np.zeros(121, np.int64)
+            np.cumsum(lens, out=off[1:])
+            tiled = bench.tiled_host(i386, int(off[-1]), gs).tobytes()
+            brute = np.array([tiled[off[h]:off[h + 1]].find(nd) >= 0 for h in range(120)], np.uint8)
+            assert np.array_equal(bench.expected_set_flags(i386, nd, gs, off), brute), (nd, gs)
+        n = 2 * m + 4321
+        expect = int(sum((n - len(nd) - int(p)) // m + 1 for p in P if p <= n - len(nd)))
+        assert expect == oracle.count(bench.tiled_host(i386, n), nd), nd
+    assert oracle.count(b"aaaaa", b"aa") == 4  # overlapping occurrences count

@@ -11,7 +11,7 @@ run() { # tool, -k expression
         > "gpurun_out/sanitizer_$1.log" 2>&1
     echo "$1 rc=$?"; tail -3 "gpurun_out/sanitizer_$1.log"
 }
-run memcheck  "kats or memchr or edge or mula or unaligned or async_entry or many_haystack or short_sweep or batched_single or pairs_mode or random_bench or count_mode"
-run racecheck "mula or unaligned or async_entry"
-run synccheck "mula or unaligned or async_entry or count_mode"
-run initcheck "kats or batched_single or ipsum_absent or memchr or edge or short_sweep or pairs_mode"
+run memcheck  "kats or memchr or edge or mula or unaligned or async_entry or many_haystack or short_sweep or batched_single or pairs_mode or random_bench or count_mode or histogram or prepared"
+run racecheck "mula or unaligned or async_entry or histogram or prepared"
+run synccheck "mula or unaligned or async_entry or count_mode or histogram"
+run initcheck "kats or batched_single or ipsum_absent or memchr or edge or short_sweep or pairs_mode or histogram or prepared or count_mode"
