@@ -332,6 +332,25 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
                           "gbs": round(hay.numel() * 5 / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1)}
         rare[repr(nd)] = row
     out["rarest_position_gbs"] = rare
+    # the histogram kernel itself: every byte of the 8 GiB haystack, and the 16 MiB sample used above
+    hrow = {}
+    for label, sample in (("whole_haystack", 0), ("sample_16MiB", 16 << 20)):
+        for _ in range(2):
+            ss._check(ss.lib().ss_b200_byte_histogram_device_async(hay.data_ptr(), hay.numel(), sample,
+                                                                   d_hist.data_ptr(),
+                                                                   torch.cuda.current_stream().cuda_stream))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            ss._check(ss.lib().ss_b200_byte_histogram_device_async(hay.data_ptr(), hay.numel(), sample,
+                                                                   d_hist.data_ptr(),
+                                                                   torch.cuda.current_stream().cuda_stream))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        hrow[label] = {"ms": round(ms, 4), "bytes_counted": int(d_hist.sum().item()),
+                       "gbs": round(int(d_hist.sum().item()) / (ms * 1e-3) / 1e9, 1)}
+    out["byte_histogram"] = hrow
 
     # SURVEY 8f-1 count mode: the same scan without the early return, every occurrence counted; the
     # expected count of the 8 GiB tiling follows from the match positions of one period

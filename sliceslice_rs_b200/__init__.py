@@ -32,7 +32,8 @@ __all__ = ["DynamicB200Searcher", "B200Searcher", "DeviceHaystack", "SearcherPan
            "launch_count", "Batch", "set_extra_anchors", "HaystackSet", "rarest_position"]
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libsliceslice_b200.so")
+# SS_B200_LIB: load another build of the same ABI instead (A/B measurements of kernel changes)
+LIB_PATH = os.environ.get("SS_B200_LIB") or os.path.join(PKG, "libsliceslice_b200.so")
 NPOS = (1 << 64) - 1
 DEVICE_NONE = 0x7FFFFFFFFFFFFFFF
 OK, E_POSITION, E_EMPTY_NEEDLE, E_ARG, E_CUDA, E_NOMEM = range(6)
