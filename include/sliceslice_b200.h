@@ -133,8 +133,10 @@ int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haystack *h, uint
 int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t *offset);
 
 /* search_in(&[u8]) with a HOST slice: the literal analogue of src/x86.rs:523.
- * Streams the haystack to the device in chunks (three device buffers, copy/scan
- * overlap) and scans it there; PCIe-bound by construction.  Pinned (cudaHostAlloc /
+ * A slice of up to 32 KiB (the reference's short-haystack regime) is copied into the calling thread's
+ * mapped pinned buffer and scanned in place over PCIe: one launch, no DMA, no events.  Longer slices
+ * stream to the device in chunks (three device buffers, copy/scan
+ * overlap) and are scanned there; PCIe-bound by construction.  Pinned (cudaHostAlloc /
  * cudaHostRegister) memory is copied directly; a pageable slice of 8 MiB or more is
  * staged through a pinned ring that a pool of memcpy worker threads fills in parallel
  * (SS_B200_HOST_THREADS: worker count, default min(7, cores-1), 0 = let the driver

@@ -89,6 +89,10 @@ extern "C" int ss_b200_set_scan_variant(int variant)
 }
 extern "C" int ss_b200_set_scan_tuning(int ctas_per_sm, int unroll, int tile_kib, int stages)
 {
+    // 0 = auto everywhere; anything else must be a value the launcher knows (scan_long.cu)
+    if (ctas_per_sm < 0 || ctas_per_sm > 32 || (unroll != 0 && unroll != 1 && unroll != 4) ||
+        (tile_kib != 0 && tile_kib != 16 && tile_kib != 32) || stages < 0 || stages > 8 || stages == 1)
+        return SS_B200_E_ARG;
     g_tuning.ctas_per_sm = ctas_per_sm;
     g_tuning.unroll = unroll;
     g_tuning.tile_kib = tile_kib;
@@ -405,7 +409,8 @@ extern "C" int ss_b200_count_in_device_async(const ss_b200_searcher *s, const vo
 }
 
 // One synchronous scan of device memory through the thread's context.
-static int find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset)
+int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
+                             int force_variant)
 {
     const size_t k = s->needle.size();
     if (k == 0) { // DynamicAvx2Searcher::N0 => true, even for an empty haystack (src/x86.rs:470,500)
@@ -433,7 +438,10 @@ static int find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t 
     a.ws = c->ws;
     a.out = (unsigned long long *)&c->slot_dev->value;
     c->slot->value = SS_RESULT_PENDING;
-    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, c->stream));
+    SsScanTuning tuning = g_tuning;
+    if (force_variant)
+        tuning.variant = force_variant;
+    SS_CUDA(ss_host_launch_scan(a, tuning, dev, c->stream));
     // spin on the mapped result word; fall back to the stream status every so often
     unsigned spins = 0;
     while (c->slot->value == SS_RESULT_PENDING) {
@@ -461,7 +469,7 @@ extern "C" int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack
 {
     if (!s || !h || !offset)
         return SS_B200_E_ARG;
-    return find_device_sync(s, h->dptr, h->len, offset);
+    return ss_capi_find_device_sync(s, h->dptr, h->len, offset, 0);
 }
 
 extern "C" int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haystack *h, uint8_t *found)
@@ -469,7 +477,7 @@ extern "C" int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haysta
     if (!s || !h || !found)
         return SS_B200_E_ARG;
     size_t off = SS_B200_NPOS;
-    int rc = find_device_sync(s, h->dptr, h->len, &off);
+    int rc = ss_capi_find_device_sync(s, h->dptr, h->len, &off, 0);
     if (rc == SS_B200_OK)
         *found = (off != SS_B200_NPOS) ? 1 : 0;
     return rc;

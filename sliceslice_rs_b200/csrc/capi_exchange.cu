@@ -129,7 +129,7 @@ extern "C" int ss_b200_find_in_device_exchange_async(const ss_b200_searcher *s, 
             return rc;
         a.ws = (SsWorkspace *)workspace;
         a.out = (unsigned long long *)((uint8_t *)workspace + 16); // local copy of this rank's own result
-            a.n_peers = (uint32_t)world;
+        a.n_peers = (uint32_t)world;
         for (int p = 0; p < world; p++)
             a.peer_slot[p] = (unsigned long long *)mailboxes[p] + row + rank;
         SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, st));

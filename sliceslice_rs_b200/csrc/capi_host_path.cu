@@ -137,6 +137,19 @@ extern "C" int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *ho
     if (rc != SS_B200_OK)
         return rc;
 
+    if (len <= SS_SMALL_HOST_MAX) {
+        // short slice (the reference's short-haystack regime, src/x86.rs:363-375): no DMA, no events --
+        // copy it into this thread's mapped pinned buffer and let the scan read it in place over PCIe;
+        // one launch and the mapped result word are all that is left of the call
+        if (!c->small_host) {
+            SS_CUDA(cudaHostAlloc((void **)&c->small_host, SS_SMALL_HOST_MAX + 32, cudaHostAllocMapped));
+            SS_CUDA(cudaHostGetDevicePointer((void **)&c->small_dev, c->small_host, 0));
+        }
+        memcpy(c->small_host, host, len);
+        memset(c->small_host + len, 0, 32 - (len & 15)); // the scan reads whole 16-byte chunks
+        return ss_capi_find_device_sync(s, c->small_dev, len, offset, 1); // direct loads, never the staged ring
+    }
+
     const size_t halo = k - 1;
     size_t chunk = host_chunk_bytes();
     // large pageable slice: stage through pinned buffers with the copy pool (smaller chunks keep the
@@ -229,7 +242,7 @@ extern "C" int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *ho
         ss_host_scan_geometry(a, chunk);
         a.ws = c->ws;
         a.out = c->chunk_results_dev + i;
-            SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, c->stream));
+        SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, c->stream));
         SS_CUDA(cudaEventRecord(c->scanned[b], c->stream));
         submitted++;
     }

@@ -60,11 +60,19 @@ struct SsThreadCtx {
     cudaEvent_t scanned[NBUF] = {nullptr, nullptr, nullptr};
     uint8_t *stage[NBUF] = {nullptr, nullptr, nullptr}; // pinned staging for pageable host haystacks
     size_t stage_cap = 0;
+    uint8_t *small_host = nullptr; // pinned + mapped copy of a short host slice (read in place by the kernel)
+    uint8_t *small_dev = nullptr;  // device view of the same memory
     unsigned long long *chunk_results = nullptr; // pinned + mapped, one per in-flight chunk
     unsigned long long *chunk_results_dev = nullptr;
     size_t chunk_results_cap = 0;
 };
 int ss_capi_get_ctx(SsThreadCtx **out);
+// one synchronous scan of device-visible memory through the calling thread's context
+// (force_variant: 0 = the process-wide tuning, 1 / 2 = that scan variant for this call)
+int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
+                             int force_variant);
+// host slices up to this size are searched in place from a mapped pinned copy (capi_host_path.cu)
+#define SS_SMALL_HOST_MAX (32u << 10)
 
 // kernel arguments for one scan of (dptr, len) with this searcher (k >= 1, len >= k)
 int ss_capi_build_args(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base, size_t start_limit,

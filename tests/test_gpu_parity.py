@@ -393,6 +393,37 @@ def test_host_path_chunked(monkeypatch, variant):
     assert oracle.find(host, nd) == 5
 
 
+def test_host_path_short_slices_in_place():
+    # host slices up to 32 KiB are searched in place from a mapped pinned copy (no DMA); lengths on both
+    # sides of that limit and of the 16-byte chunking, unaligned host pointers, needle at the very end
+    rng = np.random.default_rng(11)
+    base = rng.integers(97, 101, 70000, dtype=np.uint8)
+    for n in (1, 2, 15, 16, 17, 31, 32, 33, 4095, 4096, 32767, 32768, 32769, 40000):
+        for shift in (0, 1, 5):
+            h = base[shift:shift + n].copy()
+            hb = h.tobytes()
+            for k in (1, 2, 5, 17, 40):
+                if k > n:
+                    continue
+                nd_absent = bytes([0xEE]) * k
+                s = ss.DynamicB200Searcher.new(nd_absent)
+                assert s.find_in(h) is None and s.search_in(hb) is False
+                h2 = h.copy()
+                h2[n - k:] = 0xEE  # planted as the last k bytes
+                assert s.find_in(h2) == n - k == oracle.find(h2, nd_absent), (n, shift, k)
+                s.close()
+            nd = hb[n // 2:n // 2 + 6]
+            s = ss.DynamicB200Searcher.new(nd)
+            assert s.find_in(base[shift:shift + n]) == oracle.find(hb, nd) == _expect(hb, nd), (n, shift)
+            s.close()
+    # back-to-back calls reuse the same buffer: a shorter slice after a longer one must not see stale bytes
+    s = ss.DynamicB200Searcher.new(b"zzzz")
+    assert s.find_in(b"a" * 1000 + b"zzzz") == 1000
+    assert s.find_in(b"a" * 998 + b"zz") is None
+    assert s.find_in(b"a" * 20) is None
+    s.close()
+
+
 def test_host_path_pageable_staging_pool():
     # large pageable host slices go through the pinned staging ring filled by the copy pool
     n = (150 << 20) + 1234  # several 32 MiB chunks
