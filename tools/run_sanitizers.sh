@@ -14,4 +14,8 @@ run() { # tool, -k expression
 run memcheck  "kats or memchr or edge or mula or unaligned or async_entry or many_haystack or short_sweep or batched_single or pairs_mode or random_bench or count_mode or histogram or prepared"
 run racecheck "mula or unaligned or async_entry or histogram or prepared"
 run synccheck "mula or unaligned or async_entry or count_mode or histogram"
-run initcheck "kats or batched_single or ipsum_absent or memchr or edge or short_sweep or pairs_mode or histogram or prepared or count_mode"
+# initcheck: only tests whose haystacks are uploads (ss_b200_haystack_upload zeroes the padding) or exact
+# byte reads (histogram).  The scans read whole 16-byte chunks, so on a BORROWED buffer whose length is
+# not a multiple of 16 the last chunk includes bytes past the end (inside the allocation granule, masked
+# out before any compare counts) -- initcheck reports those by design.
+run initcheck "kats or batched_single or ipsum_absent or memchr or edge or short_sweep or pairs_mode or histogram"
