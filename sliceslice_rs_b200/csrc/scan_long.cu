@@ -3,6 +3,7 @@
 #include "ss_host.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace {
 std::atomic<uint64_t> g_launches{0};
@@ -134,7 +135,26 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
         grid = n_tiles;
     if (grid < 1)
         grid = 1;
-    fn<<<(unsigned)grid, SS_LDG_THREADS, 0, stream>>>(a);
+    // programmatic stream serialisation: this launch may begin while the previous kernel of the stream is
+    // still running; the kernel itself waits (griddepcontrol.wait) before its first global access.  Short
+    // searches issued back to back are launch-bound, and this hides most of the launch.  SS_B200_PDL=0
+    // falls back to a plain launch.
+    static const bool pdl = [] {
+        const char *v = getenv("SS_B200_PDL");
+        return !(v && atoi(v) == 0);
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(SS_LDG_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    void *args[] = {(void *)&a};
+    const cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)fn, args);
     ss_host_count_launch(1);
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -182,6 +182,14 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
     AdaptiveFilter af;
     uint32_t occ = 0; // count mode: occurrences seen by this thread
 
+    // Programmatic dependent launch (scan_long.cu launches this variant with programmatic stream
+    // serialisation): let the next kernel of the stream start launching now, and touch no global memory
+    // (haystack, workspace, result) before every earlier kernel of the stream has completed and flushed.
+    // Back-to-back short searches then overlap one launch with the previous scan; without the launch
+    // attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
         bool stop;

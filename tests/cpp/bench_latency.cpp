@@ -80,6 +80,19 @@ int main(int argc, char **argv)
             printf("long sweep (one find_in_device_async per word, one sync): %.3f ms/iteration, %.2f us/call, sum %llu\n",
                    ms, ms * 1e3 / searchers.size(), sum);
         }
+        // the same number of stream-ordered calls with ONE searcher (one kernel variant, absent needle):
+        // separates the cost of the call itself from the cost of switching kernels between launches
+        auto same = DynamicB200Searcher::new_("ipsum");
+        for (int it = 0; it < 3; it++) {
+            auto t0 = clk::now();
+            for (size_t w = 0; w < searchers.size(); w++)
+                same.find_in_device_async(hay.device_ptr(), hay.len(), 0, SS_B200_NPOS, d_ws, d_res + w, st);
+            const double enq_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+            cudaStreamSynchronize(st);
+            double ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+            printf("same searcher, %zu stream-ordered calls: %.2f us/call (host enqueue alone %.2f us)\n", searchers.size(),
+                   ms * 1e3 / searchers.size(), enq_ms * 1e3 / searchers.size());
+        }
         cudaFree(d_res);
         cudaFree(d_ws);
         cudaStreamDestroy(st);
