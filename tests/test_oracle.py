@@ -144,3 +144,25 @@ def test_random_bench_size_grid():
             if r is not None:
                 found.append((ns, hsz))
     assert found == [(1, 100), (1, 1000)]
+
+
+def test_count_restarts_the_reference_search_after_every_match(i386):
+    # checker of the count mode: overlapping occurrences included; compared with a naive count
+    import random
+
+    def naive(h, nd):
+        c, i = 0, h.find(nd)
+        while i >= 0:
+            c += 1
+            i = h.find(nd, i + 1)
+        return c
+
+    assert oracle.count(b"aaaaa", b"aa") == 4
+    assert oracle.count(b"abcabc", b"abcd") == 0 and oracle.count(b"", b"a") == 0
+    for nd in (b"e", b"th", b"segment", b"ipsum", b"descriptor table", b"  "):
+        assert oracle.count(i386[:200000], nd) == naive(i386[:200000], nd), nd
+    rng = random.Random(9)
+    for _ in range(200):
+        h = bytes(rng.choice(b"ab") for _ in range(rng.randrange(0, 300)))
+        nd = bytes(rng.choice(b"ab") for _ in range(rng.randrange(1, 6)))
+        assert oracle.count(h, nd) == naive(h, nd)
