@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_B200_ABI_VERSION 1
+#define SS_B200_ABI_VERSION 2
 
 /* "not found" for host-side offsets: usize::MAX / std::string::npos
  * (bench/sse4-strstr/src/lib.rs:12-14). */
@@ -47,12 +47,16 @@ enum ss_b200_status {
     SS_B200_E_EMPTY_NEEDLE = 2, /* Avx2Searcher::new(empty) panics, src/x86.rs:285,300 (strict ctors only) */
     SS_B200_E_ARG = 3,          /* NULL handle / pointer */
     SS_B200_E_CUDA = 4,         /* CUDA runtime error or no device; see ss_b200_last_error() */
-    SS_B200_E_NOMEM = 5
+    SS_B200_E_NOMEM = 5,
+    SS_B200_E_NCCL = 6          /* libnccl not loadable, or an NCCL call failed; see ss_b200_last_error() */
 };
 
 typedef struct ss_b200_searcher ss_b200_searcher; /* opaque, immutable after creation */
 typedef struct ss_b200_haystack ss_b200_haystack; /* opaque device-resident haystack   */
 typedef struct ss_b200_batch ss_b200_batch;       /* opaque device-resident word sets  */
+typedef struct ss_b200_ctx ss_b200_ctx;           /* opaque multi-GPU context: every GPU of the box, one process */
+typedef struct ss_b200_sharded ss_b200_sharded;   /* opaque haystack sharded over the devices of a context */
+typedef struct ss_b200_ctx_hayset ss_b200_ctx_hayset; /* opaque set of haystacks partitioned over a context */
 
 const char *ss_b200_strerror(int status);
 /* Thread-local detail string of the last SS_B200_E_CUDA on this thread. */
@@ -102,7 +106,18 @@ int ss_b200_haystack_upload(const uint8_t *host, size_t len, ss_b200_haystack **
 /* Borrow `len` bytes already in device memory (any byte alignment).  The synchronous search calls
  * run on a stream owned by the library: the bytes must be complete (no write still pending on another
  * stream) when ss_b200_search_in / ss_b200_find_in is called.  ss_b200_find_in_device_async is the
- * stream-ordered entry. */
+ * stream-ordered entry.
+ *
+ * READ PRECONDITION (differs from the reference).  The reference never touches a byte outside the
+ * borrowed slice: its last block is re-aligned to end exactly at haystack[len) (src/lib.rs:276-284,
+ * rationale src/x86.rs:257-261).  The kernels here load whole 16-byte aligned words, i.e. they read
+ * [align_down(dptr, 16), align_up(dptr + len, 16)): up to 15 bytes before and up to 15 bytes after the
+ * slice.  Those bytes never influence a result (positions outside [0, len - k] are masked before use)
+ * and the loads cannot fault: an aligned 16-byte word never crosses a page, so it lies in a page that
+ * also holds a byte of the slice, and device (and pinned host) mappings are page-granular.  What the
+ * caller must accept is that memory-checking tools (compute-sanitizer initcheck) may report those bytes
+ * as read while uninitialised, and that a slice carved out of a larger buffer has its neighbours' edge
+ * bytes loaded (never used).  This applies to every entry point that takes device memory. */
 int ss_b200_haystack_from_device(const void *dptr, size_t len, ss_b200_haystack **out);
 void ss_b200_haystack_free(ss_b200_haystack *h);
 size_t ss_b200_haystack_len(const ss_b200_haystack *h);
@@ -135,14 +150,29 @@ int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t
 /* search_in(&[u8]) with a HOST slice: the literal analogue of src/x86.rs:523.
  * A slice of up to 32 KiB (the reference's short-haystack regime) is copied into the calling thread's
  * mapped pinned buffer and scanned in place over PCIe: one launch, no DMA, no events.  Longer slices
- * stream to the device in chunks (three device buffers, copy/scan
- * overlap) and are scanned there; PCIe-bound by construction.  Pinned (cudaHostAlloc /
- * cudaHostRegister) memory is copied directly; a pageable slice of 8 MiB or more is
- * staged through a pinned ring that a pool of memcpy worker threads fills in parallel
- * (SS_B200_HOST_THREADS: worker count, default min(7, cores-1), 0 = let the driver
- * stage; SS_B200_HOST_CHUNK_MIB: chunk size, default 64 pinned / 32 pageable). */
+ * stream to the device in chunks (a ring of three device buffers sized from the slice: an eighth of
+ * it, between 4 and 64 MiB each; copy/scan overlap; the host feeds at most three chunks ahead of the
+ * results it has seen, so a match stops the feeding) and are scanned there; PCIe-bound by
+ * construction.  Pinned (cudaHostAlloc / cudaHostRegister) memory is copied directly, or -- short
+ * pinned slices, and always with ss_b200_set_host_path(2, ..) -- read in place by the scan kernel.  A
+ * pageable slice of 8 MiB or more is staged through a pinned ring that a pool of memcpy worker threads
+ * fills in parallel.  See ss_b200_set_host_path. */
 int ss_b200_search_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, uint8_t *found);
 int ss_b200_find_in_host(const ss_b200_searcher *s, const uint8_t *host, size_t len, size_t *offset);
+
+/* The same call with ONE host slice striped over every device of a context: chunk i of the slice goes
+ * to device i % ndev, every device runs its own copy/scan ring, so all PCIe links of the box carry the
+ * slice at once; the first offsets are MIN-reduced in the library.  Same semantics and result as
+ * ss_b200_find_in_host. */
+int ss_b200_find_in_host_multi(ss_b200_ctx *ctx, const ss_b200_searcher *s, const uint8_t *host, size_t len,
+                               size_t *offset);
+int ss_b200_search_in_host_multi(ss_b200_ctx *ctx, const ss_b200_searcher *s, const uint8_t *host, size_t len,
+                                 uint8_t *found);
+/* What the last ss_b200_find_in_host_multi of this context did: bytes handed to cudaMemcpyAsync, chunks
+ * submitted, chunk size, and data path (1 DMA ring, 2 in place, 3 short slice; +10 = pageable input
+ * staged through the pinned ring).  Any pointer may be NULL. */
+int ss_b200_ctx_last_host_stats(const ss_b200_ctx *ctx, uint64_t *h2d_bytes, uint64_t *chunks, uint64_t *chunk_bytes,
+                                int *mode);
 
 /* Stream-ordered scan of device memory, no host synchronisation.
  *   dptr, len     haystack bytes in device memory (any alignment)
@@ -194,6 +224,66 @@ int ss_b200_find_in_device_exchange_async(const ss_b200_searcher *s, const void 
                                           void *const *mailboxes, int world, int rank, uint64_t seq,
                                           uint64_t *d_result, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Multi-GPU from ONE process.  The reference binds plain C functions from a single
+ * process (bench/sse4-strstr/build.rs:8-23, bench/sse4-strstr/src/lib.rs:4-15, wrapper.h:7); a host that
+ * follows that pattern reaches every GPU of the box through a context.  A context is used by one thread
+ * at a time (calls on one context are serialised). */
+
+/* devices == NULL: devices 0 .. ndev-1; ndev <= 0: every visible device.  Creates, per device, the
+ * streams, workspace and mapped result slot of the synchronous calls, and enables peer access between
+ * all pairs. */
+int ss_b200_ctx_create(int ndev, const int *devices, ss_b200_ctx **out);
+void ss_b200_ctx_free(ss_b200_ctx *ctx);
+int ss_b200_ctx_device_count(const ss_b200_ctx *ctx);
+int ss_b200_ctx_device(const ss_b200_ctx *ctx, int i); /* CUDA ordinal of lane i, -1 if out of range */
+
+/* How ss_b200_search_sharded MIN-reduces the per-shard first offsets (NCCL has no bitwise OR; the
+ * minimum over first offsets gives found AND the leftmost offset):
+ *   HOST  every scan publishes into its own mapped host word; the calling thread takes the minimum
+ *         (default: nothing but the scans on the critical path)
+ *   PEER  the scan's last CTA stores its result into every device's mailbox (peer HBM over NVLink),
+ *         a one-warp kernel per device takes the minimum: the result is also complete on every GPU
+ *   NCCL  ncclAllReduce(ncclMin, ncclUint64, count 1) over communicators made with ncclCommInitAll;
+ *         libnccl.so.2 is loaded with dlopen on first use -- SS_B200_E_NCCL if that fails */
+enum ss_b200_exchange { SS_B200_EXCHANGE_HOST = 0, SS_B200_EXCHANGE_PEER = 1, SS_B200_EXCHANGE_NCCL = 2 };
+int ss_b200_ctx_set_exchange(ss_b200_ctx *ctx, int kind);
+int ss_b200_ctx_nccl_version(int *version); /* e.g. 22809; SS_B200_E_NCCL when libnccl cannot be loaded */
+
+/* One haystack as contiguous shards of start positions, shard d on device d of the context: shard d
+ * owns positions [d*per, (d+1)*per), per = ceil(len / ndev) rounded up to 16, and holds `halo` more
+ * bytes (right halo only: start positions are independent, src/lib.rs:263-274).  A needle of up to
+ * halo + 1 bytes can be searched; longer ones are SS_B200_E_ARG. */
+int ss_b200_sharded_upload(const ss_b200_ctx *ctx, const uint8_t *host, size_t len, size_t halo,
+                           ss_b200_sharded **out);
+/* Borrow shards already in device memory: dptrs[d] (on device d of the context) holds spans[d] bytes
+ * starting at global byte owned[0] + .. + owned[d-1] and owns the first owned[d] start positions. */
+int ss_b200_sharded_from_device(const ss_b200_ctx *ctx, const void *const *dptrs, const size_t *owned,
+                                const size_t *spans, ss_b200_sharded **out);
+void ss_b200_sharded_free(ss_b200_sharded *sh);
+size_t ss_b200_sharded_len(const ss_b200_sharded *sh);
+int ss_b200_sharded_shard(const ss_b200_sharded *sh, int i, const void **dptr, size_t *start, size_t *owned,
+                          size_t *span);
+
+/* DynamicAvx2Searcher::search_in over the sharded haystack (src/x86.rs:523-525): every device scans
+ * its shard concurrently, the first offsets are MIN-reduced by the context's exchange.  *found = 1/0;
+ * *global_offset (nullable) = leftmost occurrence in the whole haystack or SS_B200_NPOS. */
+int ss_b200_search_sharded(ss_b200_ctx *ctx, const ss_b200_searcher *s, const ss_b200_sharded *sh, uint8_t *found,
+                           size_t *global_offset);
+int ss_b200_find_sharded(ss_b200_ctx *ctx, const ss_b200_searcher *s, const ss_b200_sharded *sh, size_t *offset);
+
+/* Many-haystack mode over the devices of a context: the set (CSR: blob + n+1 uint64 offsets, host
+ * memory) is partitioned into contiguous index ranges of balanced bytes, one per device; every
+ * haystack lives on exactly one device, so the OR over devices is a gather of disjoint flag slices.
+ * flags[h] (host, n bytes) = search_in(haystack h). */
+int ss_b200_ctx_hayset_upload(const ss_b200_ctx *ctx, const uint8_t *blob, const uint64_t *offsets, size_t n,
+                              ss_b200_ctx_hayset **out);
+void ss_b200_ctx_hayset_free(ss_b200_ctx_hayset *hs);
+size_t ss_b200_ctx_hayset_len(const ss_b200_ctx_hayset *hs);
+int ss_b200_ctx_hayset_part(const ss_b200_ctx_hayset *hs, int i, size_t *lo, size_t *hi);
+int ss_b200_ctx_hayset_search(ss_b200_ctx *ctx, const ss_b200_searcher *s, const ss_b200_ctx_hayset *hs,
+                              uint8_t *flags);
+
 /* Many-haystack mode, stream-ordered: ONE needle against a device-resident SET of haystacks in a
  * single pass at the long-scan rate (the set is scanned as one blob; a match counts for haystack h
  * only if it lies wholly inside it).  Per haystack the result is search_in() of src/x86.rs:523.
@@ -220,6 +310,14 @@ void ss_b200_hayset_free(ss_b200_hayset *hs);
 size_t ss_b200_hayset_len(const ss_b200_hayset *hs);
 int ss_b200_hayset_search_async(const ss_b200_searcher *s, const ss_b200_hayset *hs, uint8_t *d_flags,
                                 void *workspace, void *stream);
+
+/* Bit-packed flags for the cross-GPU OR of the many-haystack mode.  Rank r holds haystacks
+ * [first_bit, first_bit + n) of a global set of total_bits haystacks: the call zeroes the whole bitmap
+ * d_words (ceil(total_bits / 32) uint32) and sets bit h of it for every local flag that is non-zero.
+ * The ranks' bit ranges are disjoint, so ncclAllReduce(ncclSum, ncclUint32) over the bitmaps is the
+ * bitwise OR NCCL lacks (/usr/include/nccl.h: sum, prod, max, min, avg) at 1 bit per haystack. */
+int ss_b200_pack_flags_async(const uint8_t *d_flags, size_t n, size_t first_bit, uint32_t *d_words, size_t total_bits,
+                             void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* Batched modes (north-star "batched many-haystack mode"; workloads:
@@ -249,6 +347,22 @@ int ss_b200_batch_search_triangular(const ss_b200_batch *b, uint32_t *bitmap, ui
  * table).  offsets[w] = first offset or UINT64_MAX (host array, n_needles). */
 int ss_b200_batch_find_all_in(const ss_b200_batch *b, const ss_b200_haystack *h, uint64_t *offsets);
 
+/* Stream-ordered forms of the three batched searches: inputs and outputs in DEVICE memory, enqueued on
+ * `stream` (cudaStream_t as void*, NULL = legacy default stream), no host synchronisation and no state
+ * shared between calls -- any number of streams may use one batch handle concurrently.  (The
+ * synchronous forms above run on the calling thread's own stream and copy the results back.)
+ *   pairs       d_pair_needle / d_pair_hay: n_pairs uint32 indices, which must be in range;
+ *               d_bitmap (nullable) ceil(n_pairs / 32) words, d_offsets (nullable) n_pairs uint64
+ *   triangular  d_bitmap ceil(W(W+1)/2 / 32) words, d_matches one uint64
+ *   find_all    dptr/len: the haystack; d_offsets n_needles uint64 (first offset or UINT64_MAX) */
+int ss_b200_batch_search_pairs_async(const ss_b200_batch *b, const uint32_t *d_pair_needle,
+                                     const uint32_t *d_pair_hay, size_t n_pairs, uint32_t *d_bitmap,
+                                     uint64_t *d_offsets, void *stream);
+int ss_b200_batch_search_triangular_async(const ss_b200_batch *b, uint32_t *d_bitmap, uint64_t *d_matches,
+                                          void *stream);
+int ss_b200_batch_find_all_in_device_async(const ss_b200_batch *b, const void *dptr, size_t len,
+                                           uint64_t *d_offsets, void *stream);
+
 /* ------------------------------------------------------------------------- */
 /* Synthetic inputs of BASELINE configs 2'/4/5, generated in HBM so that multi-
  * GiB haystacks never cross PCIe.  Bit-identical CPU copies live in oracle/.  */
@@ -271,6 +385,25 @@ int ss_b200_set_scan_tuning(int ctas_per_sm, int unroll, int tile_kib, int stage
  * (word-aligned needle offsets 4 and 8, or one of 1..3 for short needles): 0 = never, 1 or -1 =
  * adaptive per warp (default).  Changes the candidate rate only, never a result. */
 int ss_b200_set_extra_anchors(int n);
+/* The short-scan variant is launched with programmatic stream serialisation (back-to-back searches on
+ * one stream overlap each launch with the previous scan): 1 = on (default), 0 = plain launches. */
+int ss_b200_set_launch_pdl(int on);
+/* Host-slice path (ss_b200_find_in_host / _multi):
+ *   mode          0 auto (pinned slices up to 16 MiB in place, else the DMA ring), 1 always the DMA ring,
+ *                 2 pinned input read in place by the direct-load kernel, 3 in place by the TMA kernel
+ *   chunk_mib     0 auto (an eighth of a device's share of the slice, 4..64 MiB), else MiB per chunk
+ *   copy_threads  memcpy workers that stage pageable input: -1 auto (min(7, cores-1); 15 for a
+ *                 multi-device context), 0 = hand pageable memory to the driver */
+int ss_b200_set_host_path(int mode, int chunk_mib, int copy_threads);
+/* Measured host->device copy bandwidth of the current device: `bytes` of pinned memory, best of
+ * `reps` cudaMemcpyAsync (the PCIe ceiling the host-slice path is reported against). */
+int ss_b200_measure_h2d(size_t bytes, int reps, double *gb_per_s);
+/* The synchronous calls keep a per-thread, per-device lane (two streams, a 64-byte workspace, a mapped
+ * result word and -- after a host-slice search -- a staging ring sized from the slices searched).  It is
+ * released when the thread exits; ss_b200_thread_release() releases it now (the next call rebuilds what
+ * it needs).  ss_b200_thread_footprint reports what the calling thread currently holds. */
+int ss_b200_thread_release(void);
+int ss_b200_thread_footprint(size_t *device_bytes, size_t *pinned_bytes);
 /* Number of kernel launches issued by this library in this process so far. */
 uint64_t ss_b200_launch_count(void);
 

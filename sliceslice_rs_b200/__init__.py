@@ -29,14 +29,17 @@ import numpy as np
 
 __all__ = ["DynamicB200Searcher", "B200Searcher", "DeviceHaystack", "SearcherPanic", "B200Error", "lib",
            "NPOS", "DEVICE_NONE", "fill_random", "fill_tiled", "set_scan_variant", "set_scan_tuning",
-           "launch_count", "Batch", "set_extra_anchors", "HaystackSet", "rarest_position"]
+           "launch_count", "Batch", "set_extra_anchors", "HaystackSet", "rarest_position", "Context",
+           "ShardedHaystack", "ContextHaystackSet", "set_host_path", "set_launch_pdl", "measure_h2d",
+           "thread_release", "thread_footprint", "E_NCCL", "EXCHANGE_HOST", "EXCHANGE_PEER", "EXCHANGE_NCCL"]
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 # SS_B200_LIB: load another build of the same ABI instead (A/B measurements of kernel changes)
 LIB_PATH = os.environ.get("SS_B200_LIB") or os.path.join(PKG, "libsliceslice_b200.so")
 NPOS = (1 << 64) - 1
 DEVICE_NONE = 0x7FFFFFFFFFFFFFFF
-OK, E_POSITION, E_EMPTY_NEEDLE, E_ARG, E_CUDA, E_NOMEM = range(6)
+OK, E_POSITION, E_EMPTY_NEEDLE, E_ARG, E_CUDA, E_NOMEM, E_NCCL = range(7)
+EXCHANGE_HOST, EXCHANGE_PEER, EXCHANGE_NCCL = range(3)
 
 _lib = None
 
@@ -109,6 +112,36 @@ def lib() -> C.CDLL:
         "ss_b200_set_scan_tuning": (i32, [i32, i32, i32, i32]),
         "ss_b200_set_extra_anchors": (i32, [i32]),
         "ss_b200_launch_count": (u64, []),
+        "ss_b200_set_launch_pdl": (i32, [i32]),
+        "ss_b200_set_host_path": (i32, [i32, i32, i32]),
+        "ss_b200_measure_h2d": (i32, [sz, i32, C.POINTER(C.c_double)]),
+        "ss_b200_thread_release": (i32, []),
+        "ss_b200_thread_footprint": (i32, [C.POINTER(sz), C.POINTER(sz)]),
+        "ss_b200_batch_search_pairs_async": (i32, [vp, vp, vp, sz, vp, vp, vp]),
+        "ss_b200_batch_search_triangular_async": (i32, [vp, vp, vp, vp]),
+        "ss_b200_batch_find_all_in_device_async": (i32, [vp, vp, sz, vp, vp]),
+        "ss_b200_pack_flags_async": (i32, [vp, sz, sz, vp, sz, vp]),
+        "ss_b200_ctx_create": (i32, [i32, vp, pp]),
+        "ss_b200_ctx_free": (None, [vp]),
+        "ss_b200_ctx_device_count": (i32, [vp]),
+        "ss_b200_ctx_device": (i32, [vp, i32]),
+        "ss_b200_ctx_set_exchange": (i32, [vp, i32]),
+        "ss_b200_ctx_nccl_version": (i32, [C.POINTER(i32)]),
+        "ss_b200_sharded_upload": (i32, [vp, vp, sz, sz, pp]),
+        "ss_b200_sharded_from_device": (i32, [vp, vp, vp, vp, pp]),
+        "ss_b200_sharded_free": (None, [vp]),
+        "ss_b200_sharded_len": (sz, [vp]),
+        "ss_b200_sharded_shard": (i32, [vp, i32, pp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]),
+        "ss_b200_search_sharded": (i32, [vp, vp, vp, C.POINTER(C.c_uint8), C.POINTER(sz)]),
+        "ss_b200_find_sharded": (i32, [vp, vp, vp, C.POINTER(sz)]),
+        "ss_b200_find_in_host_multi": (i32, [vp, vp, vp, sz, C.POINTER(sz)]),
+        "ss_b200_search_in_host_multi": (i32, [vp, vp, vp, sz, C.POINTER(C.c_uint8)]),
+        "ss_b200_ctx_last_host_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]),
+        "ss_b200_ctx_hayset_upload": (i32, [vp, vp, vp, sz, pp]),
+        "ss_b200_ctx_hayset_free": (None, [vp]),
+        "ss_b200_ctx_hayset_len": (sz, [vp]),
+        "ss_b200_ctx_hayset_part": (i32, [vp, i32, C.POINTER(sz), C.POINTER(sz)]),
+        "ss_b200_ctx_hayset_search": (i32, [vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError here == header/library mismatch: fail loudly
@@ -124,7 +157,7 @@ def _check(rc: int) -> None:
         return
     if rc in (E_POSITION, E_EMPTY_NEEDLE):
         raise SearcherPanic(lib().ss_b200_strerror(rc).decode())
-    detail = lib().ss_b200_last_error().decode() if rc in (E_CUDA, E_NOMEM) else ""
+    detail = lib().ss_b200_last_error().decode() if rc in (E_CUDA, E_NOMEM, E_NCCL, E_ARG) else ""
     raise B200Error(f"{lib().ss_b200_strerror(rc).decode()} {detail}".strip())
 
 
@@ -315,13 +348,14 @@ class _SearcherBase:
         if stream is None:
             stream = torch.cuda.current_stream(hayset.blob.device)
         sp = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        ws = hayset.workspace_for(sp)
         if hayset.prepared:
             _check(lib().ss_b200_hayset_search_async(self._s, hayset.handle(stream), flags.data_ptr(),
-                                                     hayset.workspace.data_ptr(), sp))
+                                                     ws.data_ptr(), sp))
         else:
             _check(lib().ss_b200_search_many_async(self._s, hayset.blob.data_ptr(), hayset.offsets.data_ptr(),
                                                    len(hayset), hayset.blob_len, flags.data_ptr(),
-                                                   hayset.workspace.data_ptr(), sp))
+                                                   ws.data_ptr(), sp))
         return flags
 
     def close(self) -> None:
@@ -361,9 +395,22 @@ class HaystackSet:
         self.blob_len = int(off[-1])
         self.blob = torch.from_numpy(blob.copy()).to(device)
         self.offsets = torch.from_numpy(off.astype(np.int64)).to(device)
-        self.workspace = torch.zeros(32, dtype=torch.uint8, device=device)
+        self._ws_by_stream = {}
         self.prepared = prepared
         self._hs = None
+
+    def workspace_for(self, stream_ptr: int):
+        """The self-resetting scan workspace is per stream: searches of one set issued on different
+        streams must not share its key / ticket words."""
+        ws = self._ws_by_stream.get(stream_ptr)
+        if ws is None:
+            import torch
+
+            with torch.cuda.device(self.blob.device):
+                ws = torch.zeros(32, dtype=torch.uint8, device=self.blob.device)
+                torch.cuda.current_stream().synchronize()  # zeroed before any other stream uses it
+            self._ws_by_stream[stream_ptr] = ws
+        return ws
 
     def handle(self, stream=None):
         """The ``ss_b200_hayset`` of this set, created (hints built in stream order) on first use."""
@@ -410,7 +457,7 @@ class HaystackSet:
         self.blob_len = blob.numel()
         self.blob = blob
         self.offsets = offsets
-        self.workspace = torch.zeros(32, dtype=torch.uint8, device=blob.device)
+        self._ws_by_stream = {}
         self.prepared = prepared
         self._hs = None
         return self
@@ -518,3 +565,191 @@ def set_extra_anchors(n: int = -1) -> None:
 
 def launch_count() -> int:
     return lib().ss_b200_launch_count()
+
+
+def set_launch_pdl(on: bool = True) -> None:
+    _check(lib().ss_b200_set_launch_pdl(1 if on else 0))
+
+
+def set_host_path(mode: int = 0, chunk_mib: int = 0, copy_threads: int = -1) -> None:
+    """Host-slice path knobs (``ss_b200_set_host_path``): mode 0 auto / 1 DMA ring / 2 in place (direct
+    loads) / 3 in place (TMA); chunk size in MiB (0 = sized from the slice); memcpy workers for pageable
+    input (-1 auto, 0 = driver staging)."""
+    _check(lib().ss_b200_set_host_path(mode, chunk_mib, copy_threads))
+
+
+def measure_h2d(nbytes: int = 1 << 30, reps: int = 3) -> float:
+    """Pinned host->device cudaMemcpyAsync bandwidth of the current device in GB/s."""
+    out = C.c_double(0.0)
+    _check(lib().ss_b200_measure_h2d(nbytes, reps, C.byref(out)))
+    return out.value
+
+
+def thread_release() -> None:
+    """Free the calling thread's streams, result slot and staging ring (``ss_b200_thread_release``)."""
+    _check(lib().ss_b200_thread_release())
+
+
+def thread_footprint():
+    d, p = C.c_size_t(0), C.c_size_t(0)
+    _check(lib().ss_b200_thread_footprint(C.byref(d), C.byref(p)))
+    return d.value, p.value
+
+
+def _host_addr(haystack):
+    if _is_torch_tensor(haystack):
+        if haystack.is_cuda or not haystack.is_contiguous() or haystack.dtype.itemsize != 1:
+            raise B200Error("host tensor must be a contiguous CPU tensor of 1-byte elements")
+        return haystack.data_ptr(), haystack.numel(), haystack
+    return _host_view(haystack)
+
+
+class ShardedHaystack:
+    """One haystack as contiguous shards of start positions, one per device of a :class:`Context`
+    (``ss_b200_sharded``)."""
+
+    def __init__(self, handle, keepalive=None):
+        self._h = handle
+        self._keep = keepalive
+
+    def __len__(self) -> int:
+        return lib().ss_b200_sharded_len(self._h)
+
+    def shard(self, i: int):
+        """(device pointer, start, owned, span) of shard i."""
+        p, a, b, c = C.c_void_p(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _check(lib().ss_b200_sharded_shard(self._h, i, C.byref(p), C.byref(a), C.byref(b), C.byref(c)))
+        return p.value or 0, a.value, b.value, c.value
+
+    def close(self) -> None:
+        if self._h:
+            lib().ss_b200_sharded_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ContextHaystackSet:
+    """A set of haystacks partitioned over the devices of a :class:`Context` (``ss_b200_ctx_hayset``)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __len__(self) -> int:
+        return lib().ss_b200_ctx_hayset_len(self._h)
+
+    def part(self, i: int):
+        lo, hi = C.c_size_t(), C.c_size_t()
+        _check(lib().ss_b200_ctx_hayset_part(self._h, i, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def close(self) -> None:
+        if self._h:
+            lib().ss_b200_ctx_hayset_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """Every GPU of the box from one process (``ss_b200_ctx``): sharded device-resident haystacks,
+    one host slice striped over all PCIe links, and the many-haystack mode partitioned over the devices."""
+
+    def __init__(self, ndev: int = 0, devices=None, exchange: int = EXCHANGE_HOST):
+        h = C.c_void_p()
+        arr = None
+        if devices is not None:
+            ndev = len(devices)
+            arr = (C.c_int * ndev)(*devices)
+        _check(lib().ss_b200_ctx_create(ndev, arr, C.byref(h)))
+        self._c = h
+        if exchange != EXCHANGE_HOST:
+            self.set_exchange(exchange)
+
+    @property
+    def device_count(self) -> int:
+        return lib().ss_b200_ctx_device_count(self._c)
+
+    @property
+    def devices(self):
+        return [lib().ss_b200_ctx_device(self._c, i) for i in range(self.device_count)]
+
+    def set_exchange(self, kind: int) -> None:
+        _check(lib().ss_b200_ctx_set_exchange(self._c, kind))
+
+    def upload_sharded(self, data, halo: int = 4096) -> ShardedHaystack:
+        addr, n, keep = _host_addr(data)
+        h = C.c_void_p()
+        _check(lib().ss_b200_sharded_upload(self._c, addr, n, halo, C.byref(h)))
+        return ShardedHaystack(h)
+
+    def sharded_from_tensors(self, tensors, owned) -> ShardedHaystack:
+        """Borrow one CUDA uint8 tensor per device of the context (tensor d on device d holds
+        ``owned[d]`` start positions followed by its right halo)."""
+        n = self.device_count
+        if len(tensors) != n or len(owned) != n:
+            raise B200Error("one tensor and one owned count per device of the context")
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        ow = (C.c_size_t * n)(*[int(x) for x in owned])
+        sp = (C.c_size_t * n)(*[t.numel() for t in tensors])
+        h = C.c_void_p()
+        _check(lib().ss_b200_sharded_from_device(self._c, ptrs, ow, sp, C.byref(h)))
+        return ShardedHaystack(h, keepalive=list(tensors))
+
+    def find_sharded(self, searcher, sharded: ShardedHaystack) -> Optional[int]:
+        out = C.c_size_t(0)
+        _check(lib().ss_b200_find_sharded(self._c, searcher._s, sharded._h, C.byref(out)))
+        return None if out.value == NPOS else out.value
+
+    def search_sharded(self, searcher, sharded: ShardedHaystack) -> bool:
+        found, off = C.c_uint8(0), C.c_size_t(0)
+        _check(lib().ss_b200_search_sharded(self._c, searcher._s, sharded._h, C.byref(found), C.byref(off)))
+        return bool(found.value)
+
+    def find_in_host(self, searcher, haystack) -> Optional[int]:
+        """``search_in(&[u8])`` with one host slice striped over every device of the context."""
+        addr, n, keep = _host_addr(haystack)
+        out = C.c_size_t(0)
+        _check(lib().ss_b200_find_in_host_multi(self._c, searcher._s, addr, n, C.byref(out)))
+        return None if out.value == NPOS else out.value
+
+    def last_host_stats(self) -> dict:
+        a, b, c, m = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        _check(lib().ss_b200_ctx_last_host_stats(self._c, C.byref(a), C.byref(b), C.byref(c), C.byref(m)))
+        return {"h2d_bytes": a.value, "chunks": b.value, "chunk_bytes": c.value, "mode": m.value}
+
+    def upload_haystack_set(self, haystacks) -> ContextHaystackSet:
+        blob, off = _csr(haystacks)
+        h = C.c_void_p()
+        _check(lib().ss_b200_ctx_hayset_upload(self._c, blob.ctypes.data, off.ctypes.data, len(haystacks), C.byref(h)))
+        return ContextHaystackSet(h)
+
+    def search_haystack_set(self, searcher, hset: ContextHaystackSet) -> np.ndarray:
+        flags = np.zeros(len(hset), np.uint8)
+        _check(lib().ss_b200_ctx_hayset_search(self._c, searcher._s, hset._h, flags.ctypes.data))
+        return flags
+
+    def close(self) -> None:
+        if self._c:
+            lib().ss_b200_ctx_free(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_version() -> int:
+    v = C.c_int(0)
+    _check(lib().ss_b200_ctx_nccl_version(C.byref(v)))
+    return v.value

@@ -190,14 +190,9 @@ __device__ __noinline__ void multi_verify(const MultiArgs &m, const MultiNeedle 
     fc.l4 = d.l4;
     fc.bs = 8u * (d.pos & 3u);
     uint32_t z[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, j, fc));
     const uint8_t *nd = m.nblob + d.off;
-    if (!K1) {
-        if (!refine_alive(av, nx, z, d.k, [&](uint32_t j) { return (uint32_t)__ldg(nd + j); }))
-            return;
-    }
+    if (!exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, d.k, [&](uint32_t j) { return (uint32_t)__ldg(nd + j); }, z))
+        return;
     const long long p0 = (long long)(chunk * 16ull) - (long long)m.head;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -411,6 +406,13 @@ extern "C" int ss_b200_batch_create(const uint8_t *needle_blob, const uint64_t *
         rc = upload(&b->d_hoff, hay_off, (n_haystacks + 1) * sizeof(uint64_t));
     if (rc == SS_B200_OK)
         rc = build_multi_tables(b);
+    if (rc == SS_B200_OK) {
+        // small pageable uploads may still be in flight on the legacy stream, which the searches' own
+        // non-blocking streams do not wait for
+        cudaError_t e2 = cudaStreamSynchronize(0);
+        if (e2 != cudaSuccess)
+            rc = ss_capi_cuda_fail(e2, "cudaStreamSynchronize(batch upload)");
+    }
     if (rc != SS_B200_OK) {
         ss_b200_batch_free(b);
         return rc;
@@ -435,6 +437,136 @@ extern "C" void ss_b200_batch_free(ss_b200_batch *b)
     delete b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// stream-ordered forms: inputs and outputs in device memory, no host synchronisation, no state shared
+// between calls (any number of streams may use one batch handle concurrently)
+
+namespace {
+// empty needles are found at offset 0 (N0, src/x86.rs:500): the scan kernels never see them
+__global__ void fix_empty_needles_kernel(const unsigned long long *__restrict__ noff, unsigned long long n,
+                                         unsigned long long *__restrict__ out)
+{
+    const unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n && noff[w + 1] == noff[w])
+        out[w] = 0;
+}
+} // namespace
+
+extern "C" int ss_b200_batch_search_pairs_async(const ss_b200_batch *b, const uint32_t *d_pair_needle,
+                                                const uint32_t *d_pair_hay, size_t n_pairs, uint32_t *d_bitmap,
+                                                uint64_t *d_offsets, void *stream)
+{
+    if (!b || (n_pairs && (!d_pair_needle || !d_pair_hay)))
+        return SS_B200_E_ARG;
+    if (n_pairs == 0)
+        return SS_B200_OK;
+    SsDeviceInfo dev;
+    int rc = ss_capi_device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    unsigned long long blocks = (n_pairs + 255) / 256;
+    const unsigned long long cap = (unsigned long long)dev.sm_count * 16;
+    if (blocks > cap)
+        blocks = cap;
+    pairs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        b->d_nblob, b->d_noff, b->d_hblob, b->d_hoff, d_pair_needle, d_pair_hay, n_pairs, d_bitmap,
+        (unsigned long long *)d_offsets);
+    ss_host_count_launch(1);
+    SS_CUDA(cudaGetLastError());
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_batch_search_triangular_async(const ss_b200_batch *b, uint32_t *d_bitmap, uint64_t *d_matches,
+                                                     void *stream)
+{
+    if (!b || !d_bitmap || !d_matches)
+        return SS_B200_E_ARG;
+    // the rule pairs word i with word j >= i of ONE list: the haystack set is the list
+    const unsigned long long w = b->n_hay;
+    if (b->n_needles != b->n_hay)
+        return SS_B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    SS_CUDA(cudaMemsetAsync(d_matches, 0, 8, st));
+    if (w == 0)
+        return SS_B200_OK;
+    SsDeviceInfo dev;
+    int rc = ss_capi_device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    const unsigned long long n_pairs = w * (w + 1) / 2;
+    unsigned long long blocks = (n_pairs + 255) / 256;
+    const unsigned long long cap = (unsigned long long)dev.sm_count * 16;
+    if (blocks > cap)
+        blocks = cap;
+    // needle i is taken from the needle set, haystack j from the haystack set (for the
+    // reference's workload both hold the same length-sorted word list)
+    triangular_kernel<<<(unsigned)blocks, 256, 0, st>>>(b->d_nblob, b->d_noff, b->d_hblob, b->d_hoff, w, n_pairs,
+                                                         d_bitmap, (unsigned long long *)d_matches);
+    ss_host_count_launch(1);
+    SS_CUDA(cudaGetLastError());
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_batch_find_all_in_device_async(const ss_b200_batch *b, const void *dptr, size_t len,
+                                                      uint64_t *d_offsets, void *stream)
+{
+    if (!b || !d_offsets || (len && !dptr))
+        return SS_B200_E_ARG;
+    const size_t nn = b->n_needles;
+    if (nn == 0)
+        return SS_B200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long n = len;
+    const uint8_t *hay = (const uint8_t *)dptr;
+    SsDeviceInfo dev;
+    int rc = ss_capi_device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    SS_CUDA(cudaMemsetAsync(d_offsets, 0xFF, nn * 8, st)); // UINT64_MAX = not found; k > n stays that way
+    if (b->n_groups > 0 && n >= b->min_k) {
+        MultiArgs m;
+        memset(&m, 0, sizeof m);
+        m.hay = hay;
+        m.n = n;
+        m.head = (uint32_t)(reinterpret_cast<uintptr_t>(hay) & 15);
+        m.last_chunk = (m.head + n - 1) / 16;
+        m.nblob = b->d_nblob;
+        m.needles = b->d_multi;
+        m.groups = b->d_groups;
+        m.best = (unsigned long long *)d_offsets;
+        m.n_groups = (uint32_t)b->n_groups;
+        const unsigned long long max_end = n - b->min_k + 1;
+        const unsigned long long n_chunks = (m.head + max_end + 15) / 16;
+        const unsigned long long n_seg = (n_chunks + SS_MN_SEG_CHUNKS - 1) / SS_MN_SEG_CHUNKS;
+        if (n_seg * b->n_groups > 0x7FFFFFFFull)
+            return SS_B200_E_ARG; // haystack x needle table too large for one launch
+        multi_needle_kernel<<<(unsigned)(n_seg * b->n_groups), SS_MN_THREADS, 0, st>>>(m);
+        ss_host_count_launch(1);
+        SS_CUDA(cudaGetLastError());
+    }
+    if (b->n_multi != nn) { // some needles are empty: N0 => found at 0
+        fix_empty_needles_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(b->d_noff, nn,
+                                                                               (unsigned long long *)d_offsets);
+        ss_host_count_launch(1);
+        SS_CUDA(cudaGetLastError());
+    }
+    return SS_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// synchronous forms: host arrays in and out, on the calling thread's own stream
+
+namespace {
+struct Scratch { // per-call device scratch, released on every exit path
+    void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Scratch()
+    {
+        for (void *q : p)
+            cudaFree(q);
+    }
+};
+} // namespace
+
 extern "C" int ss_b200_batch_search_pairs(const ss_b200_batch *b, const uint32_t *pair_needle,
                                           const uint32_t *pair_hay, size_t n_pairs, uint32_t *bitmap,
                                           uint64_t *offsets)
@@ -446,19 +578,12 @@ extern "C" int ss_b200_batch_search_pairs(const ss_b200_batch *b, const uint32_t
     for (size_t p = 0; p < n_pairs; p++)
         if (pair_needle[p] >= b->n_needles || pair_hay[p] >= b->n_hay)
             return SS_B200_E_ARG;
-    SsDeviceInfo dev;
-    int rc = ss_capi_device_info(dev);
+    SsLane *lane = nullptr;
+    int rc = ss_capi_get_lane(&lane);
     if (rc != SS_B200_OK)
         return rc;
-    // per-call device scratch, released on every exit path
-    struct Scratch {
-        void *p[4] = {nullptr, nullptr, nullptr, nullptr};
-        ~Scratch()
-        {
-            for (void *q : p)
-                cudaFree(q);
-        }
-    } sc;
+    cudaStream_t st = lane->stream;
+    Scratch sc;
     const size_t words = (n_pairs + 31) / 32;
     SS_CUDA(cudaMalloc(&sc.p[0], n_pairs * 4));
     SS_CUDA(cudaMalloc(&sc.p[1], n_pairs * 4));
@@ -466,22 +591,16 @@ extern "C" int ss_b200_batch_search_pairs(const ss_b200_batch *b, const uint32_t
     if (offsets)
         SS_CUDA(cudaMalloc(&sc.p[3], n_pairs * 8));
     uint32_t *d_pn = (uint32_t *)sc.p[0], *d_ph = (uint32_t *)sc.p[1], *d_bm = (uint32_t *)sc.p[2];
-    unsigned long long *d_off = (unsigned long long *)sc.p[3];
-    SS_CUDA(cudaMemcpy(d_pn, pair_needle, n_pairs * 4, cudaMemcpyHostToDevice));
-    SS_CUDA(cudaMemcpy(d_ph, pair_hay, n_pairs * 4, cudaMemcpyHostToDevice));
-    unsigned long long blocks = (n_pairs + 255) / 256;
-    const unsigned long long cap = (unsigned long long)dev.sm_count * 16;
-    if (blocks > cap)
-        blocks = cap;
-    pairs_kernel<<<(unsigned)blocks, 256>>>(b->d_nblob, b->d_noff, b->d_hblob, b->d_hoff, d_pn, d_ph, n_pairs, d_bm,
-                                           d_off);
-    ss_host_count_launch(1);
-    SS_CUDA(cudaGetLastError());
+    SS_CUDA(cudaMemcpyAsync(d_pn, pair_needle, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaMemcpyAsync(d_ph, pair_hay, n_pairs * 4, cudaMemcpyHostToDevice, st));
+    rc = ss_b200_batch_search_pairs_async(b, d_pn, d_ph, n_pairs, d_bm, (uint64_t *)sc.p[3], st);
+    if (rc != SS_B200_OK)
+        return rc;
     if (bitmap)
-        SS_CUDA(cudaMemcpy(bitmap, d_bm, words * 4, cudaMemcpyDeviceToHost));
+        SS_CUDA(cudaMemcpyAsync(bitmap, d_bm, words * 4, cudaMemcpyDeviceToHost, st));
     if (offsets)
-        SS_CUDA(cudaMemcpy(offsets, d_off, n_pairs * 8, cudaMemcpyDeviceToHost));
-    SS_CUDA(cudaDeviceSynchronize());
+        SS_CUDA(cudaMemcpyAsync(offsets, sc.p[3], n_pairs * 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
     return SS_B200_OK;
 }
 
@@ -489,7 +608,6 @@ extern "C" int ss_b200_batch_search_triangular(const ss_b200_batch *b, uint32_t 
 {
     if (!b || !bitmap)
         return SS_B200_E_ARG;
-    // the rule pairs word i with word j >= i of ONE list: the haystack set is the list
     const unsigned long long w = b->n_hay;
     if (b->n_needles != b->n_hay)
         return SS_B200_E_ARG;
@@ -497,12 +615,15 @@ extern "C" int ss_b200_batch_search_triangular(const ss_b200_batch *b, uint32_t 
         *matches = 0;
     if (w == 0)
         return SS_B200_OK;
-    SsDeviceInfo dev;
-    int rc = ss_capi_device_info(dev);
+    SsLane *lane = nullptr;
+    int rc = ss_capi_get_lane(&lane);
     if (rc != SS_B200_OK)
         return rc;
+    cudaStream_t st = lane->stream;
     const unsigned long long n_pairs = w * (w + 1) / 2;
     const size_t words = (size_t)((n_pairs + 31) / 32);
+    // the bitmap scratch is kept with the handle (1.3 MB for the reference's word list); calls that share
+    // a handle are serialised here -- the _async form has no such state
     std::lock_guard<std::mutex> lk(b->mu);
     if (b->bitmap_words < words) {
         cudaFree(b->d_bitmap);
@@ -513,22 +634,13 @@ extern "C" int ss_b200_batch_search_triangular(const ss_b200_batch *b, uint32_t 
     }
     if (!b->d_count)
         SS_CUDA(cudaMalloc((void **)&b->d_count, 8));
-    uint32_t *d_bm = b->d_bitmap;
-    unsigned long long *d_m = b->d_count;
-    SS_CUDA(cudaMemsetAsync(d_m, 0, 8, 0));
-    unsigned long long blocks = (n_pairs + 255) / 256;
-    const unsigned long long cap = (unsigned long long)dev.sm_count * 16;
-    if (blocks > cap)
-        blocks = cap;
-    // needle i is taken from the needle set, haystack j from the haystack set (for the
-    // reference's workload both hold the same length-sorted word list)
-    triangular_kernel<<<(unsigned)blocks, 256>>>(b->d_nblob, b->d_noff, b->d_hblob, b->d_hoff, w, n_pairs, d_bm,
-                                                  d_m);
-    ss_host_count_launch(1);
-    SS_CUDA(cudaGetLastError());
-    SS_CUDA(cudaMemcpy(bitmap, d_bm, words * 4, cudaMemcpyDeviceToHost));
+    rc = ss_b200_batch_search_triangular_async(b, b->d_bitmap, (uint64_t *)b->d_count, st);
+    if (rc != SS_B200_OK)
+        return rc;
+    SS_CUDA(cudaMemcpyAsync(bitmap, b->d_bitmap, words * 4, cudaMemcpyDeviceToHost, st));
     unsigned long long m = 0;
-    SS_CUDA(cudaMemcpy(&m, d_m, 8, cudaMemcpyDeviceToHost));
+    SS_CUDA(cudaMemcpyAsync(&m, b->d_count, 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
     if (matches)
         *matches = m;
     return SS_B200_OK;
@@ -545,43 +657,19 @@ extern "C" int ss_b200_batch_find_all_in(const ss_b200_batch *b, const ss_b200_h
     const size_t nn = b->n_needles;
     if (nn == 0)
         return SS_B200_OK;
-    const unsigned long long n = ss_b200_haystack_len(h);
-    const uint8_t *hay = (const uint8_t *)ss_b200_haystack_device_ptr(h);
-    SsDeviceInfo dev;
-    int rc = ss_capi_device_info(dev);
+    SsLane *lane = nullptr;
+    int rc = ss_capi_get_lane(&lane);
     if (rc != SS_B200_OK)
         return rc;
-
-    std::vector<unsigned long long> best(nn, SS_PAIR_NONE);
-    if (b->n_groups > 0 && n >= b->min_k) {
-        std::lock_guard<std::mutex> lk(b->mu);
-        if (!b->d_best)
-            SS_CUDA(cudaMalloc((void **)&b->d_best, nn * 8));
-        SS_CUDA(cudaMemsetAsync(b->d_best, 0xFF, nn * 8, 0));
-        MultiArgs m;
-        memset(&m, 0, sizeof m);
-        m.hay = hay;
-        m.n = n;
-        m.head = (uint32_t)(reinterpret_cast<uintptr_t>(hay) & 15);
-        m.last_chunk = (m.head + n - 1) / 16;
-        m.nblob = b->d_nblob;
-        m.needles = b->d_multi;
-        m.groups = b->d_groups;
-        m.best = b->d_best;
-        m.n_groups = (uint32_t)b->n_groups;
-        const unsigned long long max_end = n - b->min_k + 1;
-        const unsigned long long n_chunks = (m.head + max_end + 15) / 16;
-        const unsigned long long n_seg = (n_chunks + SS_MN_SEG_CHUNKS - 1) / SS_MN_SEG_CHUNKS;
-        if (n_seg * b->n_groups > 0x7FFFFFFFull)
-            return SS_B200_E_ARG; // haystack x needle table too large for one launch
-        multi_needle_kernel<<<(unsigned)(n_seg * b->n_groups), SS_MN_THREADS>>>(m);
-        ss_host_count_launch(1);
-        SS_CUDA(cudaGetLastError());
-        SS_CUDA(cudaMemcpy(best.data(), b->d_best, nn * 8, cudaMemcpyDeviceToHost));
-    }
-    for (size_t w = 0; w < nn; w++) {
-        const unsigned long long k = b->h_noff[w + 1] - b->h_noff[w];
-        offsets[w] = (k == 0) ? 0 : best[w]; // N0 => found at 0; k > n stays NONE
-    }
+    cudaStream_t st = lane->stream;
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (!b->d_best)
+        SS_CUDA(cudaMalloc((void **)&b->d_best, nn * 8));
+    rc = ss_b200_batch_find_all_in_device_async(b, ss_b200_haystack_device_ptr(h), ss_b200_haystack_len(h),
+                                                (uint64_t *)b->d_best, st);
+    if (rc != SS_B200_OK)
+        return rc;
+    SS_CUDA(cudaMemcpyAsync(offsets, b->d_best, nn * 8, cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
     return SS_B200_OK;
 }

@@ -44,6 +44,7 @@ extern "C" const char *ss_b200_strerror(int status)
     case SS_B200_E_ARG: return "invalid argument";
     case SS_B200_E_CUDA: return "CUDA error or no usable device";
     case SS_B200_E_NOMEM: return "out of memory";
+    case SS_B200_E_NCCL: return "NCCL error or libnccl not loadable";
     default: return "unknown status";
     }
 }
@@ -53,9 +54,16 @@ extern "C" int ss_b200_abi_version(void) { return SS_B200_ABI_VERSION; }
 // ---------------------------------------------------------------------------------------------
 // process-wide tuning + per-device facts
 
-static SsScanTuning g_tuning;
-static std::mutex g_dev_mutex;
-static std::map<int, SsDeviceInfo> g_devs;
+// The setters may be called while other threads search: every field is an atomic and each search works
+// on one snapshot (ss_capi_tuning).
+namespace {
+struct AtomicTuning {
+    std::atomic<int> variant{0}, ctas_per_sm{0}, unroll{0}, tile_kib{0}, stages{0}, extra_anchors{-1}, pdl{1};
+    std::atomic<int> host_mode{0}, host_chunk_mib{0}, host_copy_threads{-1};
+} g_tuning;
+std::mutex g_dev_mutex;
+std::map<int, SsDeviceInfo> g_devs;
+} // namespace
 
 static int device_info(SsDeviceInfo &out)
 {
@@ -69,8 +77,6 @@ static int device_info(SsDeviceInfo &out)
         SS_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
         SS_CUDA(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         SS_CUDA(cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-        const char *v = getenv("SS_B200_LONG_VARIANT");
-        d.auto_long_variant = (v && atoi(v) == 1) ? 1 : 2;
         it = g_devs.emplace(dev, d).first;
     }
     out = it->second;
@@ -78,7 +84,26 @@ static int device_info(SsDeviceInfo &out)
 }
 
 int ss_capi_device_info(SsDeviceInfo &out) { return device_info(out); }
-const SsScanTuning &ss_capi_tuning() { return g_tuning; }
+SsScanTuning ss_capi_tuning()
+{
+    SsScanTuning t;
+    t.variant = g_tuning.variant.load(std::memory_order_relaxed);
+    t.ctas_per_sm = g_tuning.ctas_per_sm.load(std::memory_order_relaxed);
+    t.unroll = g_tuning.unroll.load(std::memory_order_relaxed);
+    t.tile_kib = g_tuning.tile_kib.load(std::memory_order_relaxed);
+    t.stages = g_tuning.stages.load(std::memory_order_relaxed);
+    t.extra_anchors = g_tuning.extra_anchors.load(std::memory_order_relaxed);
+    t.pdl = g_tuning.pdl.load(std::memory_order_relaxed);
+    return t;
+}
+SsHostPathTuning ss_capi_host_tuning()
+{
+    SsHostPathTuning t;
+    t.mode = g_tuning.host_mode.load(std::memory_order_relaxed);
+    t.chunk_mib = g_tuning.host_chunk_mib.load(std::memory_order_relaxed);
+    t.copy_threads = g_tuning.host_copy_threads.load(std::memory_order_relaxed);
+    return t;
+}
 
 extern "C" int ss_b200_set_scan_variant(int variant)
 {
@@ -104,6 +129,22 @@ extern "C" int ss_b200_set_extra_anchors(int n)
     if (n < -1 || n > 1)
         return SS_B200_E_ARG;
     g_tuning.extra_anchors = n;
+    return SS_B200_OK;
+}
+extern "C" int ss_b200_set_launch_pdl(int on)
+{
+    if (on != 0 && on != 1)
+        return SS_B200_E_ARG;
+    g_tuning.pdl = on;
+    return SS_B200_OK;
+}
+extern "C" int ss_b200_set_host_path(int mode, int chunk_mib, int copy_threads)
+{
+    if (mode < 0 || mode > 2 || chunk_mib < 0 || chunk_mib > 4096 || copy_threads < -1 || copy_threads > 256)
+        return SS_B200_E_ARG;
+    g_tuning.host_mode = mode;
+    g_tuning.host_chunk_mib = chunk_mib;
+    g_tuning.host_copy_threads = copy_threads;
     return SS_B200_OK;
 }
 extern "C" uint64_t ss_b200_launch_count(void) { return ss_host_launch_count(); }
@@ -187,6 +228,11 @@ extern "C" int ss_b200_haystack_upload(const uint8_t *host, size_t len, ss_b200_
     cudaError_t e = cudaMemset(d + len, 0, alloc - len);
     if (e == cudaSuccess && len)
         e = cudaMemcpy(d, host, len, cudaMemcpyHostToDevice);
+    // Both calls go to the legacy default stream and may return before the bytes have landed (memset is
+    // asynchronous, a pageable copy of <= 64 KiB returns once it is staged); the searches run on the
+    // library's own non-blocking streams, which do not wait for the legacy stream.  Finish here.
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(0);
     if (e != cudaSuccess) {
         cudaFree(d);
         return cuda_fail(e, "cudaMemcpy(haystack)");
@@ -228,29 +274,144 @@ extern "C" size_t ss_b200_haystack_len(const ss_b200_haystack *h) { return h ? h
 extern "C" const void *ss_b200_haystack_device_ptr(const ss_b200_haystack *h) { return h ? h->dptr : nullptr; }
 
 // ---------------------------------------------------------------------------------------------
-// per-thread, per-device context for the synchronous calls
+// lanes: per-device resources of the synchronous calls
 
-static thread_local std::map<int, SsThreadCtx> t_ctx;
+int SsLane::init(int dev)
+{
+    SsDeviceGuard guard(dev);
+    SS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    SS_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    SS_CUDA(cudaMalloc(&ws, 64));
+    SS_CUDA(cudaMemsetAsync(ws, 0, 64, stream));
+    SS_CUDA(cudaHostAlloc((void **)&slot, sizeof(SsHostSlot), cudaHostAllocMapped | cudaHostAllocPortable));
+    slot->value = 0;
+    slot->pad = 0;
+    SS_CUDA(cudaHostGetDevicePointer((void **)&slot_dev, (void *)slot, 0));
+    SS_CUDA(cudaStreamSynchronize(stream));
+    device = dev;
+    return SS_B200_OK;
+}
 
-int ss_capi_get_ctx(SsThreadCtx **out)
+void SsLane::release()
+{
+    if (device < 0 && !stream && !ws)
+        return;
+    // at process teardown the runtime may already be gone: every call below then fails harmlessly
+    SsDeviceGuard guard(device);
+    if (stream)
+        cudaStreamSynchronize(stream);
+    if (copy_stream)
+        cudaStreamSynchronize(copy_stream);
+    for (int b = 0; b < NBUF; b++) {
+        if (dbuf[b])
+            cudaFree(dbuf[b]);
+        if (stage[b])
+            cudaFreeHost(stage[b]);
+        if (copied[b])
+            cudaEventDestroy(copied[b]);
+        if (scanned[b])
+            cudaEventDestroy(scanned[b]);
+        dbuf[b] = stage[b] = nullptr;
+        copied[b] = scanned[b] = nullptr;
+    }
+    dbuf_cap = stage_cap = 0;
+    if (small_host)
+        cudaFreeHost(small_host);
+    small_host = small_dev = nullptr;
+    if (chunk_results)
+        cudaFreeHost(chunk_results);
+    chunk_results = chunk_results_dev = nullptr;
+    chunk_results_cap = 0;
+    if (slot)
+        cudaFreeHost((void *)slot);
+    slot = slot_dev = nullptr;
+    if (ws)
+        cudaFree(ws);
+    ws = nullptr;
+    if (stream)
+        cudaStreamDestroy(stream);
+    if (copy_stream)
+        cudaStreamDestroy(copy_stream);
+    stream = copy_stream = nullptr;
+    device = -1;
+    cudaGetLastError();
+}
+
+size_t SsLane::pinned_bytes() const
+{
+    return stage_cap * NBUF + (small_host ? SS_SMALL_HOST_MAX + 32 : 0) + chunk_results_cap * 8 +
+           (slot ? sizeof(SsHostSlot) : 0);
+}
+
+// The calling thread's lanes, one per device it has searched on.  The map's destructor runs at thread
+// exit and releases the CUDA resources (a host that churns threads leaks nothing);
+// ss_b200_thread_release() does the same on demand.
+static thread_local std::map<int, SsLane> t_lanes;
+
+int ss_capi_get_lane(SsLane **out)
 {
     int dev = -1;
     SS_CUDA(cudaGetDevice(&dev));
-    SsThreadCtx &c = t_ctx[dev];
+    SsLane &c = t_lanes[dev];
     if (c.device < 0) {
-        SS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        SS_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-        SS_CUDA(cudaMalloc(&c.ws, sizeof(SsWorkspace)));
-        SS_CUDA(cudaMemset(c.ws, 0, sizeof(SsWorkspace)));
-        SS_CUDA(cudaHostAlloc((void **)&c.slot, sizeof(SsHostSlot), cudaHostAllocMapped));
-        c.slot->value = 0;
-        c.slot->pad = 0;
-        SS_CUDA(cudaHostGetDevicePointer((void **)&c.slot_dev, (void *)c.slot, 0));
-        SS_CUDA(cudaDeviceSynchronize());
-        c.device = dev;
+        int rc = c.init(dev);
+        if (rc != SS_B200_OK) {
+            c.release();
+            t_lanes.erase(dev);
+            return rc;
+        }
     }
     *out = &c;
     return SS_B200_OK;
+}
+
+extern "C" int ss_b200_thread_release(void)
+{
+    t_lanes.clear();
+    return SS_B200_OK;
+}
+
+extern "C" int ss_b200_thread_footprint(size_t *device_bytes, size_t *pinned_bytes)
+{
+    size_t d = 0, p = 0;
+    for (auto &kv : t_lanes) {
+        d += kv.second.device_bytes();
+        p += kv.second.pinned_bytes();
+    }
+    if (device_bytes)
+        *device_bytes = d;
+    if (pinned_bytes)
+        *pinned_bytes = p;
+    return SS_B200_OK;
+}
+
+int ss_capi_wait_slot(volatile unsigned long long *word, unsigned long long pending, cudaStream_t stream)
+{
+    // spin on the mapped result word; fall back to the stream status every so often
+    unsigned spins = 0;
+    while (*word == pending) {
+        if ((++spins & 0x3FF) == 0) {
+            cudaError_t e = cudaStreamQuery(stream);
+            if (e == cudaSuccess)
+                break; // everything on the stream retired: the mapped write is visible now
+            if (e != cudaErrorNotReady)
+                return cuda_fail(e, "scan kernel");
+        }
+    }
+    if (*word == pending) {
+        SS_CUDA(cudaStreamSynchronize(stream));
+        if (*word == pending) {
+            t_last_error = "scan kernel retired without publishing a result";
+            return SS_B200_E_CUDA;
+        }
+    }
+    return SS_B200_OK;
+}
+
+// one 8-byte store in stream order; the slot may be device memory or a mapped pinned host word
+__global__ void store_u64_kernel(unsigned long long *dst, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
 }
 
 static int needle_on_device(const ss_b200_searcher *s, int dev, const uint8_t **out)
@@ -261,6 +422,8 @@ static int needle_on_device(const ss_b200_searcher *s, int dev, const uint8_t **
         uint8_t *d = nullptr;
         SS_CUDA(cudaMalloc(&d, s->needle.size() + 16));
         cudaError_t e = cudaMemcpy(d, s->needle.data(), s->needle.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(0); // a small pageable copy may still be in flight (see haystack_upload)
         if (e != cudaSuccess) {
             cudaFree(d);
             return cuda_fail(e, "cudaMemcpy(needle)");
@@ -308,8 +471,12 @@ extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const voi
     // trivial outcomes are still delivered in stream order through the result slot
     if (k == 0 || len < k || start_limit == 0) {
         // N0 => true at 0 (src/x86.rs:500); n < k => false (src/x86.rs:357-359, src/lib.rs:131-133)
+        // (a store kernel, not a memcpy: d_result may be a mapped host word, and the call must stay legal
+        // under stream capture)
         const unsigned long long v = (k == 0) ? (unsigned long long)base_offset : SS_NONE_U64;
-        SS_CUDA(cudaMemcpyAsync(d_result, &v, sizeof v, cudaMemcpyHostToDevice, st));
+        store_u64_kernel<<<1, 1, 0, st>>>((unsigned long long *)d_result, v);
+        ss_host_count_launch(1);
+        SS_CUDA(cudaGetLastError());
         return SS_B200_OK;
     }
     SsDeviceInfo dev;
@@ -322,7 +489,7 @@ extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const voi
         return rc;
     a.ws = (SsWorkspace *)workspace;
     a.out = (unsigned long long *)d_result;
-    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
+    SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, st));
     return SS_B200_OK;
 }
 
@@ -369,7 +536,7 @@ int ss_capi_search_many(const ss_b200_searcher *s, const void *d_blob, const uin
     a.n_seg = n_haystacks;
     a.seg_hint = d_hint;
     a.n_gran = n_gran;
-    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
+    SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, st));
     return SS_B200_OK;
 }
 
@@ -404,11 +571,39 @@ extern "C" int ss_b200_count_in_device_async(const ss_b200_searcher *s, const vo
     a.ws = (SsWorkspace *)workspace;
     a.out = (unsigned long long *)((uint8_t *)workspace + 16); // scratch result slot
     a.count = (unsigned long long *)d_count;
-    SS_CUDA(ss_host_launch_scan(a, g_tuning, dev, st));
+    SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, st));
     return SS_B200_OK;
 }
 
-// One synchronous scan of device memory through the thread's context.
+// One synchronous scan of device-visible memory on a given lane (its device is made current for the call).
+int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
+                         int force_variant)
+{
+    SsDeviceGuard guard(c->device);
+    SsDeviceInfo dev;
+    int rc = device_info(dev);
+    if (rc != SS_B200_OK)
+        return rc;
+    ScanArgs a;
+    rc = ss_capi_build_args(s, dptr, len, 0, (size_t)-1, dev.device, a);
+    if (rc != SS_B200_OK)
+        return rc;
+    a.ws = c->ws;
+    a.out = (unsigned long long *)&c->slot_dev->value;
+    c->slot->value = SS_RESULT_PENDING;
+    SsScanTuning tuning = ss_capi_tuning();
+    if (force_variant)
+        tuning.variant = force_variant;
+    SS_CUDA(ss_host_launch_scan(a, tuning, dev, c->stream));
+    rc = ss_capi_wait_slot(&c->slot->value, SS_RESULT_PENDING, c->stream);
+    if (rc != SS_B200_OK)
+        return rc;
+    const unsigned long long v = c->slot->value;
+    *offset = (v == SS_NONE_U64) ? SS_B200_NPOS : (size_t)v;
+    return SS_B200_OK;
+}
+
+// One synchronous scan of device memory through the calling thread's lane.
 int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
                              int force_variant)
 {
@@ -423,46 +618,11 @@ int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t
     }
     if (k > 0xFFFFFFFFull)
         return SS_B200_E_ARG;
-    SsDeviceInfo dev;
-    int rc = device_info(dev);
+    SsLane *c = nullptr;
+    int rc = ss_capi_get_lane(&c);
     if (rc != SS_B200_OK)
         return rc;
-    SsThreadCtx *c = nullptr;
-    rc = ss_capi_get_ctx(&c);
-    if (rc != SS_B200_OK)
-        return rc;
-    ScanArgs a;
-    rc = ss_capi_build_args(s, dptr, len, 0, (size_t)-1, dev.device, a);
-    if (rc != SS_B200_OK)
-        return rc;
-    a.ws = c->ws;
-    a.out = (unsigned long long *)&c->slot_dev->value;
-    c->slot->value = SS_RESULT_PENDING;
-    SsScanTuning tuning = g_tuning;
-    if (force_variant)
-        tuning.variant = force_variant;
-    SS_CUDA(ss_host_launch_scan(a, tuning, dev, c->stream));
-    // spin on the mapped result word; fall back to the stream status every so often
-    unsigned spins = 0;
-    while (c->slot->value == SS_RESULT_PENDING) {
-        if ((++spins & 0x3FF) == 0) {
-            cudaError_t e = cudaStreamQuery(c->stream);
-            if (e == cudaSuccess)
-                break; // kernel retired: the mapped write is visible now
-            if (e != cudaErrorNotReady)
-                return cuda_fail(e, "scan kernel");
-        }
-    }
-    if (c->slot->value == SS_RESULT_PENDING) {
-        SS_CUDA(cudaStreamSynchronize(c->stream));
-        if (c->slot->value == SS_RESULT_PENDING) {
-            t_last_error = "scan kernel retired without publishing a result";
-            return SS_B200_E_CUDA;
-        }
-    }
-    const unsigned long long v = c->slot->value;
-    *offset = (v == SS_NONE_U64) ? SS_B200_NPOS : (size_t)v;
-    return SS_B200_OK;
+    return ss_capi_find_on_lane(c, s, dptr, len, offset, force_variant);
 }
 
 extern "C" int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t *offset)

@@ -105,3 +105,62 @@ extern "C" int ss_b200_hayset_search_async(const ss_b200_searcher *s, const ss_b
     return ss_capi_search_many(s, hs->blob, hs->offsets, hs->n, hs->blob_len, d_flags, workspace, hs->hint,
                                hs->n_gran, stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Bit-packed flags for the cross-GPU OR.  Every haystack of a partitioned set lives on one rank, so the
+// ranks' flags occupy disjoint bit ranges of one global bitmap: each rank packs its byte flags into its
+// own range (all other bits of its copy zero) and the copies are combined with ncclAllReduce(ncclSum)
+// on uint32 words -- with disjoint bits a sum is the bitwise OR NCCL lacks -- moving 1 bit per haystack
+// instead of the 1 byte per haystack x world of a MAX-reduced byte array.
+
+namespace {
+// word w of the bitmap covers global haystacks [32w, 32w+32); this rank holds [bit0, bit0 + n)
+__global__ void pack_flags_kernel(const uint8_t *__restrict__ flags, unsigned long long n, unsigned long long bit0,
+                                  uint32_t *__restrict__ words)
+{
+    const unsigned long long w0 = bit0 >> 5, w1 = (bit0 + n + 31) >> 5;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long w = w0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += stride) {
+        uint32_t v = 0;
+        const long long g0 = (long long)(w << 5) - (long long)bit0; // local index of the word's bit 0
+        if (g0 >= 0 && (unsigned long long)g0 + 32 <= n && ((reinterpret_cast<uintptr_t>(flags + g0) & 15) == 0)) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(flags + g0);
+            const uint4 b = *reinterpret_cast<const uint4 *>(flags + g0 + 16);
+            const uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                // four byte flags (any non-zero value counts) -> four bits
+                const uint32_t nz = ~swar_zero_exact(q[t]) & 0x80808080u;
+                v |= (((nz >> 7) * 0x00204081u) >> 21 & 0xFu) << (4 * t);
+            }
+        } else {
+            for (int t = 0; t < 32; t++) {
+                const long long i = g0 + t;
+                if (i >= 0 && (unsigned long long)i < n && flags[i])
+                    v |= 1u << t;
+            }
+        }
+        words[w] = v;
+    }
+}
+} // namespace
+
+extern "C" int ss_b200_pack_flags_async(const uint8_t *d_flags, size_t n, size_t first_bit, uint32_t *d_words,
+                                        size_t total_bits, void *stream)
+{
+    if (!d_words || (n && !d_flags) || first_bit + n > total_bits)
+        return SS_B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_words = (total_bits + 31) / 32;
+    SS_CUDA(cudaMemsetAsync(d_words, 0, n_words * 4, st));
+    if (n == 0)
+        return SS_B200_OK;
+    const unsigned long long cnt = ((first_bit + n + 31) >> 5) - (first_bit >> 5);
+    unsigned long long blocks = (cnt + 255) / 256;
+    if (blocks > 148ull * 8)
+        blocks = 148ull * 8;
+    pack_flags_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_flags, n, first_bit, d_words);
+    ss_host_count_launch(1);
+    SS_CUDA(cudaGetLastError());
+    return SS_B200_OK;
+}

@@ -175,8 +175,8 @@ extern "C" int ss_b200_haystack_byte_histogram(const ss_b200_haystack *h, size_t
 {
     if (!h || !hist)
         return SS_B200_E_ARG;
-    SsThreadCtx *c = nullptr;
-    int rc = ss_capi_get_ctx(&c);
+    SsLane *c = nullptr;
+    int rc = ss_capi_get_lane(&c);
     if (rc != SS_B200_OK)
         return rc;
     uint64_t *d_hist = nullptr;

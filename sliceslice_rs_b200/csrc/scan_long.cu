@@ -137,12 +137,9 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
         grid = 1;
     // programmatic stream serialisation: this launch may begin while the previous kernel of the stream is
     // still running; the kernel itself waits (griddepcontrol.wait) before its first global access.  Short
-    // searches issued back to back are launch-bound, and this hides most of the launch.  SS_B200_PDL=0
-    // falls back to a plain launch.
-    static const bool pdl = [] {
-        const char *v = getenv("SS_B200_PDL");
-        return !(v && atoi(v) == 0);
-    }();
+    // searches issued back to back are launch-bound, and this hides most of the launch
+    // (ss_b200_set_launch_pdl(0) falls back to a plain launch).
+    const bool pdl = t.pdl != 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(SS_LDG_THREADS);

@@ -145,6 +145,12 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
     if (XK != 0)
         af.end_tile(extras, slow ? 4u : 0u);
     if (slow) {
+        // many-haystack mode over a prepared set: a step that lies inside one already-flagged haystack
+        // has nothing left to decide
+        if (a.seg_hint != nullptr &&
+            many_step_covered(a, (long long)(cw * 16ull) - (long long)a.head,
+                              (long long)((cw + U * 32) * 16ull) - (long long)a.head - 1))
+            return false;
         if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
             for (int u = 0; u < U; u++)
@@ -189,6 +195,8 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
     // attribute both instructions are no-ops.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    cta_best_reset();
+    __syncthreads();
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
@@ -241,6 +249,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
         }
         mbar_fence_init();
     }
+    cta_best_reset();
     __syncthreads();
 
     if (warp == CW) {
@@ -330,6 +339,13 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
                 if (XK != 0)
                     trips += slow ? 1u : 0u;
                 if (slow) {
+                    // many-haystack mode over a prepared set: a step that lies inside one already-flagged
+                    // haystack has nothing left to decide (warp-uniform)
+                    const unsigned long long sc0 = tile_c0 + (unsigned long long)(lc0 - lane);
+                    if (a.seg_hint != nullptr &&
+                        many_step_covered(a, (long long)(sc0 * 16ull) - (long long)a.head,
+                                          (long long)((sc0 + 32 * U) * 16ull) - (long long)a.head - 1))
+                        continue;
                     if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
                         for (int u = 0; u < U; u++)

@@ -159,8 +159,29 @@ static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const u
     return true;
 }
 
-// Many-haystack mode: mark the haystack that wholly contains the match at blob position i.
-static __device__ __noinline__ void segment_hit(const ScanArgs &a, unsigned long long i)
+// The CTA's best (smallest) verified offset of a first-match search, in shared memory: every matching
+// lane improves it with a shared-memory atomic, and only a lane that lowers it touches the global word
+// (a common word matches in every tile at once; thousands of same-address global atomics were what a
+// found search paid for).  Reset by the kernels before the first tile.
+static __shared__ unsigned long long ss_cta_best;
+
+__device__ __forceinline__ void cta_best_reset()
+{
+    if (threadIdx.x == 0)
+        ss_cta_best = ~0ull;
+}
+
+__device__ __forceinline__ uint8_t ld_relaxed_u8(const uint8_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return (uint8_t)v;
+}
+
+// Many-haystack mode: mark the haystack that wholly contains the match at blob position i.  Returns the
+// first start position behind which a match can no longer fall into that haystack (so the caller can
+// skip the other occurrences inside it), or 0 when nothing was flagged.
+static __device__ __noinline__ unsigned long long segment_hit(const ScanArgs &a, unsigned long long i)
 {
     // h = last segment with seg_off[h] <= i
     unsigned long long lo = 0, hi = a.n_seg; // invariant: seg_off[lo] <= i < seg_off[hi]
@@ -179,37 +200,73 @@ static __device__ __noinline__ void segment_hit(const ScanArgs &a, unsigned long
         else
             hi = mid;
     }
-    if (i + a.k <= __ldg(a.seg_off + lo + 1))
+    const unsigned long long e = __ldg(a.seg_off + lo + 1);
+    if (i + a.k <= e) {
         a.seg_flags[lo] = 1;
+        return e - a.k + 1;
+    }
+    return 0;
 }
+
+// Many-haystack mode over a prepared set: do all start positions p_first .. p_last (one warp step) lie
+// in ONE haystack that is already flagged?  Then the step has nothing left to decide and its hit path
+// is skipped.  A needle present in most haystacks matches in almost every step; after the first match
+// inside a haystack everything else in it is redundant (one per haystack suffices, src/lib.rs:242-244
+// applied per haystack).  Called with warp-uniform arguments (the loads broadcast).  A flag that another
+// thread is setting right now may still read 0: that only costs the work.
+static __device__ __noinline__ bool many_step_covered(const ScanArgs &a, long long p_first, long long p_last)
+{
+    if (p_first < 0)
+        p_first = 0;
+    if (p_last >= (long long)a.end)
+        p_last = (long long)a.end - 1;
+    if (p_last < p_first)
+        return true; // no start position at all
+    const unsigned long long g = (unsigned long long)p_first >> SS_HINT_SHIFT;
+    unsigned long long h = __ldg(a.seg_hint + g); // haystack holding the first byte of the granule
+    unsigned long long e = __ldg(a.seg_off + h + 1);
+    for (int probes = 0; e <= (unsigned long long)p_first; probes++) { // walk to the haystack holding p_first
+        if (probes == 6 || h + 1 >= a.n_seg)
+            return false;
+        h++;
+        e = __ldg(a.seg_off + h + 1);
+    }
+    if ((unsigned long long)p_last + a.k > e)
+        return false; // the step reaches into the next haystack
+    return ld_relaxed_u8(a.seg_flags + h) != 0;
+}
+
+#define SS_MODE_FIND 0  // first match: leftmost offset, early exit
+#define SS_MODE_COUNT 1 // every occurrence counted, no early exit
+#define SS_MODE_MANY 2  // many-haystack mode: flag the haystack holding the match, no early exit
 
 // Hit path for one chunk whose SWAR flag fired -- the ctz loop + memcmp of src/lib.rs:216-248, done
 // without touching memory: the lane already holds the 32 haystack bytes [16c, 16c+32) in registers,
-// which cover needle bytes 0..16 of every start position of the chunk.  `z` keeps one bit per still-
-// alive start position; each round slides the window by one byte and ANDs in the exact compare with
-// the next needle byte for all 16 positions at once.  Natural-text false candidates die in the first
-// round or two.  Survivors (17 bytes equal) of longer needles finish from global memory.
+// which cover needle bytes 0..16 of every start position of the chunk (exact_alive).  Natural-text false
+// candidates leave after a few needle bytes.  Survivors (17 bytes equal) of longer needles finish from
+// global memory.
 // Returns the number of occurrences counted (count mode only; 0 in every other mode): the caller keeps
 // the running total in a register and adds it to *a.count once per warp at the end of the kernel
 // (count_flush) -- one atomic per occurrence on a single address would serialise in L2.
-template <int WS, bool BSZ, bool K1>
-__device__ __noinline__ uint32_t verify_chunk(const ScanArgs &a, uint4 av, uint4 nx, uint4 lo, uint4 hi,
-                                              unsigned long long chunk)
+template <int WS, bool BSZ, bool K1, int MODE>
+__device__ __noinline__ uint32_t verify_chunk_mode(const ScanArgs &a, uint4 av, uint4 nx, uint4 lo, uint4 hi,
+                                                   unsigned long long chunk)
 {
     FilterConsts fc;
     fc.f4 = a.f4;
     fc.l4 = a.l4;
     fc.bs = a.bs;
     uint32_t z[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, j, fc));
-    if (!K1) {
-        if (!refine_alive(av, nx, z, a.k, [&](uint32_t j) { return (uint32_t)a.needle_inline[j]; }))
-            return 0;
+    if (!exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, a.k, [&](uint32_t j) { return (uint32_t)a.needle_inline[j]; }, z))
+        return 0;
+    const long long p0 = (long long)(chunk * 16ull) - (long long)a.head; // position of byte 0 of the chunk
+    if (MODE == SS_MODE_COUNT && (K1 || a.k <= 17u) && p0 >= 0 && (unsigned long long)p0 + 16ull <= a.end) {
+        // every surviving bit is an occurrence (the register window covered the whole needle) and every
+        // position of the chunk is in range: no bit loop
+        return __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
     }
     uint32_t occ = 0;
-    const long long p0 = (long long)(chunk * 16ull) - (long long)a.head; // position of byte 0 of the chunk
+    unsigned long long flagged_until = 0; // many mode: positions below this lie in a haystack flagged just now
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         uint32_t zz = z[j];
@@ -219,25 +276,45 @@ __device__ __noinline__ uint32_t verify_chunk(const ScanArgs &a, uint4 av, uint4
             const long long i = p0 + 4 * j + (bit >> 3);
             if (i < 0 || (unsigned long long)i >= a.end)
                 continue;
+            if (MODE == SS_MODE_MANY && (unsigned long long)i < flagged_until)
+                continue;
             if (K1 || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
-                if (a.count) {
-                    // count mode: every occurrence (overlapping ones included), no early exit
-                    occ++;
+                if (MODE == SS_MODE_COUNT) {
+                    occ++; // every occurrence (overlapping ones included), no early exit
                     continue;
                 }
-                if (a.seg_off) {
-                    // many-haystack mode: the blob is a concatenation of haystacks; a match counts for
-                    // haystack h iff it lies entirely inside [seg_off[h], seg_off[h+1]).  No early exit.
-                    segment_hit(a, (unsigned long long)i);
+                if (MODE == SS_MODE_MANY) {
+                    // the blob is a concatenation of haystacks; a match counts for haystack h iff it lies
+                    // entirely inside [seg_off[h], seg_off[h+1]).  No early exit.
+                    flagged_until = segment_hit(a, (unsigned long long)i);
                     continue;
                 }
-                atomicMax(&a.ws->key, ~(unsigned long long)i);
-                __threadfence();
+                // first-match mode: CTA-level best first, the global word only when this lane lowered it.
+                // No fence: `key` is only ever touched with atomics and relaxed loads, and the acq_rel
+                // ticket of scan_finish (behind a CTA barrier) orders every atomicMax before the final read.
+                const unsigned long long old = atomicMin(&ss_cta_best, (unsigned long long)i);
+                if ((unsigned long long)i < old)
+                    atomicMax(&a.ws->key, ~(unsigned long long)i);
                 return 0; // ascending order: later positions of this chunk cannot be smaller
             }
         }
     }
     return occ;
+}
+
+// Mode dispatch (launch-uniform): one specialised hit path per mode.
+template <int WS, bool BSZ, bool K1>
+__device__ __forceinline__ uint32_t verify_chunk(const ScanArgs &a, const uint4 &av, const uint4 &nx, const uint4 &lo,
+                                                 const uint4 &hi, unsigned long long chunk)
+{
+    if (a.count)
+        return verify_chunk_mode<WS, BSZ, K1, SS_MODE_COUNT>(a, av, nx, lo, hi, chunk);
+    if (a.seg_off) {
+        verify_chunk_mode<WS, BSZ, K1, SS_MODE_MANY>(a, av, nx, lo, hi, chunk);
+        return 0;
+    }
+    verify_chunk_mode<WS, BSZ, K1, SS_MODE_FIND>(a, av, nx, lo, hi, chunk);
+    return 0;
 }
 
 // Count mode epilogue: add the warp's occurrences to *a.count with one atomic.  Called by whole,

@@ -93,31 +93,51 @@ SS_UNROLL
     return acc & 0x80808080u;
 }
 
-// Register-window refinement of the hit path.  `z` holds 0x80 in the byte of every start position of
-// the chunk that is still alive (initially: the positions that pass the exact two-anchor filter);
-// av||nx are the 32 haystack bytes from the chunk start.  Round j slides the window by one byte and
-// keeps a position alive only if hay[i + j] == needle[j], for all 16 positions at once; needle bytes
-// 1 .. min(k-1, 16) are covered (position 15 + offset 16 is the last byte of the window).  Returns
-// false as soon as nothing is alive.  `needle_at(j)` yields needle byte j.
-template <class NeedleAt>
-SS_HD bool refine_alive(const uint4 &av, const uint4 &nx, uint32_t (&z)[4], uint32_t k, NeedleAt needle_at)
+// Exact match mask of the hit path, out of registers.  av||nx are the 32 haystack bytes from the chunk
+// start, which cover needle bytes 0..16 of all 16 start positions of the chunk.  The XOR differences of
+// every compared byte pair are OR-ed into one accumulator word per 4 positions -- acc byte == 0 <=>
+// hay[i + j] == needle[j] for every j compared so far -- starting from the two anchors (filter_word) and
+// adding needle bytes 1 .. min(k - 1, 16): one funnel shift + one LOP3 per word and needle byte, one exact
+// zero-byte test at the end.  This is the analogue of the reference's constant-length memcmp arms
+// (src/lib.rs:222-241) for all 16 positions at once.  z[t] receives 0x80 in the byte of every start
+// position whose first min(k, 17) bytes equal the needle's; returns false when there is none (checked
+// every fourth needle byte, so false candidates of natural text leave early).
+// `needle_at(j)` yields needle byte j.
+template <int WS, bool BSZ, bool K1, class NeedleAt>
+SS_HD bool exact_alive(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi, const FilterConsts &fc,
+                       uint32_t k, NeedleAt needle_at, uint32_t (&z)[4])
 {
-    uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
-    const uint32_t jmax = k - 1 < 16u ? k - 1 : 16u;
-    for (uint32_t j = 1; j <= jmax; j++) {
+    const uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
+    uint32_t acc[4];
 SS_UNROLL
-        for (int t = 0; t < 7; t++)
-            w[t] = ss_funnel_r(w[t], w[t + 1], 8);
-        w[7] >>= 8;
-        const uint32_t n4 = 0x01010101u * needle_at(j);
-        uint32_t any = 0;
+    for (int t = 0; t < 4; t++)
+        acc[t] = filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, t, fc);
+    if (!K1) {
+        const uint32_t jmax = k - 1 < 16u ? k - 1 : 16u;
 SS_UNROLL
-        for (int t = 0; t < 4; t++) {
-            z[t] &= swar_zero_exact(w[t] ^ n4);
-            any |= z[t];
+        for (uint32_t j = 1; j <= 16u; j++) {
+            if (j > jmax)
+                break;
+            const uint32_t n4 = 0x01010101u * needle_at(j);
+            const uint32_t wo = j >> 2, sh = 8u * (j & 3u); // window shifted by j bytes = wo words + sh bits
+SS_UNROLL
+            for (uint32_t t = 0; t < 4; t++) {
+                const uint32_t x = sh ? ss_funnel_r(w[t + wo], w[t + wo + 1], sh) : w[t + wo];
+                acc[t] |= x ^ n4;
+            }
+            if ((j & 3u) == 0u && j < jmax) {
+                const uint32_t any = (swar_zero_term(acc[0]) | swar_zero_term(acc[1]) | swar_zero_term(acc[2]) |
+                                      swar_zero_term(acc[3])) & 0x80808080u;
+                if (!any)
+                    return false;
+            }
         }
-        if (!any)
-            return false;
     }
-    return true;
+    uint32_t any = 0;
+SS_UNROLL
+    for (int t = 0; t < 4; t++) {
+        z[t] = swar_zero_exact(acc[t]);
+        any |= z[t];
+    }
+    return any != 0;
 }

@@ -13,6 +13,7 @@ struct SsScanTuning {
     int tile_kib = 0;    // TMA: 16 or 32; 0 auto
     int stages = 0;      // TMA ring depth; 0 auto
     int extra_anchors = -1; // 0 = never use extra anchors, -1 = auto (adaptive, see AdaptiveFilter)
+    int pdl = 1;         // short-scan variant launched with programmatic stream serialisation (1) or plainly (0)
 };
 
 struct SsDeviceInfo {
@@ -20,7 +21,7 @@ struct SsDeviceInfo {
     int sm_count = 0;
     int max_smem_optin = 0;
     int smem_per_sm = 0;
-    int auto_long_variant = 1; // variant picked by "auto" for long haystacks
+    int auto_long_variant = 2; // variant picked by "auto" for long haystacks (TMA ring; measured)
 };
 
 using SsLdgFn = void (*)(const ScanArgs);

@@ -9,8 +9,11 @@ src/lib.rs:263-274 carries no state between chunks except the early return):
   ``all_reduce(MIN)`` over the global first offsets (``DEVICE_NONE`` = INT64_MAX = not found),
   which yields both the OR of the per-shard match flags and the exact leftmost offset.
   NCCL has no bitwise OR (nccl.h: sum, prod, max, min, avg), hence MIN.
-* **many haystacks** -- haystack index ranges per rank (length-balanced), needles replicated;
-  per-haystack uint8 flags reduced with ``all_reduce(MAX)``.
+* **many haystacks** -- haystack index ranges per rank (length-balanced), needles replicated.  Every
+  haystack lives on one rank, so the ranks' flags are disjoint: each rank bit-packs its slice into its
+  own bit range of one global bitmap (``ss_b200_pack_flags_async``) and the bitmaps are combined with
+  ``all_reduce(SUM)`` on int32 words -- a sum of disjoint bits is the bitwise OR NCCL lacks -- at 1 bit
+  per haystack (the first version MAX-reduced 1 byte per haystack x world).
 
 The partition arithmetic and the reductions are backend-agnostic (tested with gloo,
 world_size 2, on CPU); the scans themselves only run on CUDA.
@@ -66,12 +69,55 @@ def reduce_first_offset(local, group=None) -> Optional[int]:
 
 
 def reduce_flags(flags, group=None):
-    """all_reduce(MAX) over per-haystack uint8 match flags (each haystack lives on one rank)."""
+    """all_reduce(MAX) over per-haystack uint8 match flags (each haystack lives on one rank).
+    Kept for byte-flag consumers and CPU backends; the CUDA path uses :func:`reduce_packed_flags`."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
     return flags
+
+
+def pack_flags_reference(local_flags, first_bit: int, total_bits: int):
+    """numpy statement of ``ss_b200_pack_flags_async``: int32 words of a ``total_bits`` bitmap with bit
+    ``first_bit + i`` set iff ``local_flags[i] != 0`` (all other bits zero)."""
+    import numpy as np
+
+    bits = np.zeros(((total_bits + 31) // 32) * 32, np.uint8)
+    lf = np.asarray(local_flags)
+    bits[first_bit:first_bit + lf.size] = lf != 0
+    return np.packbits(bits, bitorder="little").view(np.int32)
+
+
+def unpack_flags(words, total_bits: int):
+    """Inverse of the packing: int32 bitmap words (numpy or CPU tensor) -> ``total_bits`` uint8 flags."""
+    import numpy as np
+
+    w = words.numpy() if hasattr(words, "numpy") else np.asarray(words)
+    return np.unpackbits(np.ascontiguousarray(w).view(np.uint8), bitorder="little")[:total_bits]
+
+
+def reduce_packed_flags(words, group=None, async_op: bool = False):
+    """all_reduce(SUM) over int32 bitmap words whose set bits are disjoint between ranks == bitwise OR."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return None
+
+
+def pack_flags_async(local_flags, first_bit: int, words, total_bits: int, stream=None) -> None:
+    """``ss_b200_pack_flags_async`` on CUDA tensors: zero ``words`` (int32, ceil(total_bits/32)) and set
+    this rank's bit range from its uint8 flags."""
+    import torch
+
+    from . import _check, lib
+
+    if stream is None:
+        stream = torch.cuda.current_stream(words.device)
+    _check(lib().ss_b200_pack_flags_async(local_flags.data_ptr() if local_flags.numel() else None,
+                                          local_flags.numel(), int(first_bit), words.data_ptr(), int(total_bits),
+                                          stream.cuda_stream))
 
 
 class ShardedSearch:
@@ -91,16 +137,22 @@ class ShardedSearch:
         self.peer = PeerExchange(group) if exchange == "peer" else None
 
     def find_async(self, searcher, stream=None):
-        """Enqueue scan + exchange on the current stream; returns the device result tensor."""
+        """Enqueue scan + exchange on ``stream`` (default: the current stream); returns the device
+        result tensor.  The collective is issued under the same stream as the scan, so the MIN never
+        reads the result word before the scan has written it."""
+        import torch
         import torch.distributed as dist
 
+        if stream is None:
+            stream = torch.cuda.current_stream(self.shard.device)
         if self.peer is not None:
             return self.peer.find_async(searcher, self.shard, self.start, self.owned, self.workspace, self.result,
                                         stream=stream)
         searcher.find_in_async(self.shard, self.result, self.workspace, base_offset=self.start,
                                start_limit=self.owned, stream=stream)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.result, op=dist.ReduceOp.MIN, group=self.group)
+            with torch.cuda.stream(stream):
+                dist.all_reduce(self.result, op=dist.ReduceOp.MIN, group=self.group)
         return self.result
 
     def find(self, searcher) -> Optional[int]:
@@ -199,8 +251,9 @@ class PeerExchange:
 
 class ShardedHaystackSet:
     """Many-haystack mode over several GPUs: haystack index ranges per rank (length-balanced,
-    :func:`partition_by_length`), needles replicated, one global uint8 flag array whose per-rank
-    slices are OR-ed with ``all_reduce(MAX)``."""
+    :func:`partition_by_length`), needles replicated.  Each rank scans its own haystacks, bit-packs its
+    flags into its bit range of the global bitmap, and the bitmaps are OR-ed with ``all_reduce(SUM)``
+    (disjoint bits; 1 bit per haystack on the wire)."""
 
     def __init__(self, haystacks, rank: int = 0, world: int = 1, group=None, device="cuda"):
         import torch
@@ -211,14 +264,23 @@ class ShardedHaystackSet:
         self.group = group
         self.lo, self.hi = partition_by_length([len(h) for h in haystacks], world)[rank]
         self.local = HaystackSet(haystacks[self.lo:self.hi], device=device)
-        self.flags = torch.zeros(self.total, dtype=torch.uint8, device=device)
+        self.local_flags = torch.zeros(max(self.hi - self.lo, 1), dtype=torch.uint8, device=device)
+        self.words = torch.zeros((self.total + 31) // 32, dtype=torch.int32, device=device)
 
     def search_async(self, searcher, stream=None):
-        """flags[h] = searcher.search_in(haystack h) for every haystack of the global set."""
-        self.flags.zero_()
-        if self.hi > self.lo:
-            searcher.search_many_async(self.local, self.flags[self.lo:self.hi], stream=stream)
-        return reduce_flags(self.flags, self.group)
+        """Bitmap words (int32 CUDA tensor): bit h = searcher.search_in(haystack h) for every haystack of
+        the global set.  Everything is enqueued on ``stream`` (default: the current stream)."""
+        import torch
+
+        if stream is None:
+            stream = torch.cuda.current_stream(self.words.device)
+        n_local = self.hi - self.lo
+        if n_local > 0:
+            searcher.search_many_async(self.local, self.local_flags[:n_local], stream=stream)
+        pack_flags_async(self.local_flags[:n_local], self.lo, self.words, self.total, stream=stream)
+        with torch.cuda.stream(stream):
+            reduce_packed_flags(self.words, self.group)
+        return self.words
 
     def search(self, searcher):
-        return self.search_async(searcher).cpu().numpy().astype(bool)
+        return unpack_flags(self.search_async(searcher).cpu(), self.total).astype(bool)

@@ -1,11 +1,11 @@
 // test_filter_host.cu -- CPU emulation of the scan built from the SAME arithmetic the kernels compile
-// (sliceslice_rs_b200/csrc/ss_filter.cuh: filter_word, chunk_flag_x, swar_zero_exact, refine_alive),
+// (sliceslice_rs_b200/csrc/ss_filter.cuh: filter_word, chunk_flag_x, swar_zero_exact, exact_alive),
 // checked against a naive search.  Runs without a GPU (host code only).
 //
 // For every random case (alphabet 2..4, haystack 0..400 bytes, needle 1..40 bytes, every head alignment
 // class, random `position`) and every extra-anchor kind the needle offers, the emulation walks the
 // 16-byte chunks exactly as a lane does -- clamped loads, second-anchor window at +q, register-window
-// refinement, range check -- and asserts:
+// exact compare, range check -- and asserts:
 //   * no false negatives: a chunk that holds the start of a real match always raises its filter flag,
 //     with and without the extra anchors;
 //   * the verified positions are exactly the naive match positions (so first offset and count agree).
@@ -57,12 +57,13 @@ static bool run_case(const Case &t, const std::vector<long long> &truth)
         const uint32_t flag_extra = chunk_flag_x<WS, BSZ, K1, XK>(av, nx, lo, hi, fc);
         // hit path, as verify_chunk
         std::vector<long long> here;
-        uint32_t z[4];
-        for (int j = 0; j < 4; j++)
-            z[j] = swar_zero_exact(filter_word<WS, BSZ, K1, 0>(av, nx, lo, hi, j, fc));
-        bool alive = true;
-        if (!K1)
-            alive = refine_alive(av, nx, z, t.k, [&](uint32_t j) { return (uint32_t)t.needle[j]; });
+        uint32_t z[4] = {0, 0, 0, 0};
+        const bool alive = exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, t.k,
+                                                    [&](uint32_t j) { return (uint32_t)t.needle[j]; }, z);
+        if (!alive && (z[0] | z[1] | z[2] | z[3])) {
+            printf("exact_alive returned false with live positions\n");
+            return false;
+        }
         const long long p0 = (long long)(c * 16) - (long long)t.head;
         for (int j = 0; alive && j < 4; j++)
             for (int b = 0; b < 4; b++)

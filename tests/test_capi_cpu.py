@@ -36,7 +36,7 @@ def test_header_symbols_are_exported():
     raw = C.CDLL(ss.LIB_PATH)
     for name in sorted(declared):
         assert hasattr(raw, name), f"{name} declared in include/sliceslice_b200.h but not exported"
-    assert ss.lib().ss_b200_abi_version() == 1
+    assert ss.lib().ss_b200_abi_version() == 2
 
 
 def test_no_torch_or_python_symbols_in_the_abi():

@@ -32,6 +32,7 @@ def _gpu():
     yield
     ss.set_scan_variant(0)
     ss.set_scan_tuning(0, 0, 0, 0)
+    ss.set_host_path(0, 0, -1)
 
 
 @pytest.fixture(params=VARIANTS, ids=["ldg", "tma"])
@@ -379,8 +380,8 @@ def test_early_exit_returns_leftmost_of_many(variant):
 # host-slice entry, async entry, shards, threads
 
 
-def test_host_path_chunked(monkeypatch, variant):
-    monkeypatch.setenv("SS_B200_HOST_CHUNK_MIB", "1")
+def test_host_path_chunked(variant):
+    ss.set_host_path(0, 1, -1)  # 1 MiB chunks: several chunks, ring wrap-around, chunk-boundary straddles
     n = (5 << 20) + 77
     host = oracle.fill_random(0, n, SEED_HAY)
     nd = bytes([1, 0xFF, 3, 4, 5, 6, 7])
@@ -391,6 +392,7 @@ def test_host_path_chunked(monkeypatch, variant):
         assert s.find_in(host) == spot
         assert s.search_in(host) is True
     assert oracle.find(host, nd) == 5
+    ss.set_host_path(0, 0, -1)
 
 
 def test_host_path_short_slices_in_place():

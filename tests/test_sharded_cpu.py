@@ -13,7 +13,8 @@ import torch.multiprocessing as mp
 
 import oracle
 from sliceslice_rs_b200 import DEVICE_NONE
-from sliceslice_rs_b200.sharded import partition_by_length, reduce_first_offset, reduce_flags, shard_bounds
+from sliceslice_rs_b200.sharded import (pack_flags_reference, partition_by_length, reduce_first_offset, reduce_flags,
+                                        reduce_packed_flags, shard_bounds, unpack_flags)
 
 
 def test_shard_bounds_cover_every_start_position_once():
@@ -87,10 +88,15 @@ def _worker(rank, world, port, hay, needle, ret):
         flags = torch.zeros(len(hays), dtype=torch.uint8)
         for i in range(lo, hi):
             flags[i] = 1 if oracle.search_in(hays[i], needle) else 0
+        # the cheaper form of the same OR: each rank packs its own slice into its bit range of one
+        # bitmap (all other bits zero) and the bitmaps are SUM-reduced -- disjoint bits, so SUM == OR
+        words = torch.from_numpy(pack_flags_reference(flags[lo:hi].numpy(), lo, len(hays)).copy())
+        reduce_packed_flags(words)
         reduce_flags(flags)
         if rank == 0:
             ret["offset"] = got
             ret["flags"] = flags.tolist()
+            ret["packed_flags"] = unpack_flags(words, len(hays)).tolist()
             ret["exp_flags"] = [1 if needle in x else 0 for x in hays]
     finally:
         dist.destroy_process_group()
@@ -115,3 +121,20 @@ def test_gloo_world2_min_reduce(case):
         mp.spawn(_worker, args=(2, _free_port(), hay, needle, ret), nprocs=2, join=True)
         assert ret["offset"] == (None if exp < 0 else exp)
         assert ret["flags"] == ret["exp_flags"]
+        assert ret["packed_flags"] == ret["exp_flags"]
+
+
+def test_packed_flags_are_disjoint_and_round_trip():
+    rng = np.random.default_rng(7)
+    for total in (1, 31, 32, 33, 1000, 4097):
+        flags = (rng.integers(0, 3, total) == 0).astype(np.uint8) * rng.integers(1, 255, total).astype(np.uint8)
+        for world in (1, 2, 3, 8):
+            cuts = sorted(rng.integers(0, total + 1, world - 1).tolist())
+            bounds = [0] + cuts + [total]
+            acc = np.zeros((total + 31) // 32, np.int64)
+            for r in range(world):
+                lo, hi = bounds[r], bounds[r + 1]
+                w = pack_flags_reference(flags[lo:hi], lo, total)
+                assert not (acc.astype(np.uint32) & w.view(np.uint32)).any()  # disjoint: SUM == OR, no carries
+                acc += w.view(np.uint32)
+            assert np.array_equal(unpack_flags(acc.astype(np.uint32), total), (flags != 0).astype(np.uint8))
