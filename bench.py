@@ -14,9 +14,16 @@ needed between steps.  One step = one search = one kernel launch per GPU.
              the torch stream, CUDA events, max over ranks).  N > 1: rank r owns the start
              positions of global bytes [r*S, (r+1)*S) plus a k-1 byte right halo, and every step
              ends with the 8-byte NCCL all_reduce(MIN) of the first offsets (weak scaling).
-  e2e        the same search through ss_b200_find_in_host on a pinned HOST buffer: chunked
+  e2e        the same search through the C-ABI host-slice call on a pinned HOST buffer: chunked
              host->device copies, scans and the result read are all inside the timed region.
+             N = 1: ss_b200_find_in_host.  N > 1: rank 0 alone calls ss_b200_find_in_host_multi on ONE
+             host slice of N x the per-GPU size, striped by the library over all N GPUs / PCIe links
+             (the other ranks wait on a CPU barrier).  e2e.roofline puts it against the pinned
+             host->device copy bandwidth measured in the same run.
   roofline   achieved HBM GB/s of the scan kernel (per-launch CUDA events) / measured copy peak.
+  parity     before anything is timed the needle is PLANTED (last k bytes of the last rank; straddling
+             a rank boundary; in rank 0 and in a later rank at once) and searched through every
+             exchange; expected and reported offsets are printed.
   cpu_baseline  the C restatement of DynamicAvx2Searcher (oracle/, the checker) timed on this
              box's host cores over a bounded sample of the same workload (rank 0, N = 1).
 
@@ -65,6 +72,8 @@ def parse_args():
                    help="single = one haystack sharded by start position (the headline); many = the batched "
                         "many-haystack mode: every GPU holds its own set of haystacks, per-haystack flags are "
                         "OR-ed across GPUs with all_reduce(MAX)")
+    p.add_argument("--sustained-steps", type=int, default=300,
+                   help="a second, longer timed run for the sustained (power-capped) rate; 0 = skip")
     p.add_argument("--no-extras", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -104,6 +113,16 @@ def committed_traffic():
             return json.load(f)
     except Exception:
         return None
+
+
+def workload_config(args, world: int) -> dict:
+    """The `config` object, identical for both arms (the reference arm times a bounded sample of this
+    workload; what the sample was is said in its cpu_baseline.sample, not here)."""
+    k = len(args.needle.encode())
+    return {"workload": f"i386 long-haystack: data/i386.txt tiled to {args.gib:g} GiB per GPU, needle "
+                        f"{args.needle!r} (absent => full scan), DynamicAvx2Searcher::new semantics",
+            "haystack_bytes_per_gpu": int(args.gib * (1 << 30)), "n_gpus": world, "needle_len": k, "position": k - 1,
+            "l2": "haystack >> L2 (126 MB): every step streams from memory, no flush needed"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -265,18 +284,17 @@ def reference_arm(args):
         assert oracle.find(hay[:n1], needle) is None
         one.append(time.perf_counter() - t1)
     single = n1 / min(one) / 1e9
-    sample = (f"i386.txt tiled to {gib:g} GiB in host DRAM (bounded sample of the {args.gib:g} GiB/GPU workload), "
-              f"needle {args.needle!r} absent, {cores} threads over contiguous slices with a k-1 halo")
+    sample = (f"i386.txt tiled to {gib:g} GiB in host DRAM (bounded sample of the {args.gib:g} GiB/GPU workload; "
+              f"a GB/s rate, so it compares with the full-size figure), needle {args.needle!r} absent, {cores} threads "
+              f"over contiguous slices with a k-1 halo; C restatement of DynamicAvx2Searcher (gcc -O3 -mavx2)")
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"i386 long-haystack: data/i386.txt tiled to {args.gib:g} GiB per GPU, needle "
-                               f"{args.needle!r} (absent => full scan), DynamicAvx2Searcher::new semantics",
-                   "haystack_bytes_per_gpu": int(args.gib * (1 << 30)), "needle_len": len(needle), "position": len(needle) - 1,
-                   "reference_path": "CPU AVX2 (C restatement of DynamicAvx2Searcher), all host threads, on a bounded "
-                                     "sample of the workload", "sample_bytes": n},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "sample_bytes": n,
                          "single_thread": {"value": round(single, 3), "cores": 1,
                                            "sample": f"first {n1 / (1 << 30):g} GiB of the same buffer, best of 3"}},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -508,18 +526,22 @@ def expected_set_flags(i386: bytes, needle: bytes, global_start: int, offsets):
     return ((s - r + cand + k) <= e).astype(np.uint8)
 
 
-def many_mode(args, ss, torch, dist, world, rank, local):
+def many_mode_run(args, ss, torch, dist, world, rank, local, steps, with_clocks=True):
     """North-star batched mode: the haystack SET is partitioned across the GPUs (each rank holds its own
-    haystacks, needles replicated), one pass per needle at the long-scan rate, per-haystack uint8 flags
-    OR-ed over ranks with all_reduce(MAX) (NCCL has no bitwise OR).  Weak scaling: --gib per GPU."""
+    haystacks, needles replicated), one pass per needle at the long-scan rate.  Every haystack lives on
+    one rank, so the per-rank flags are disjoint: each rank bit-packs its slice into its bit range of one
+    global bitmap and the bitmaps are OR-ed with all_reduce(SUM) on int32 words (NCCL has no bitwise OR; a
+    sum of disjoint bits is one) -- 1 bit per haystack on the wire.  Weak scaling: --gib per GPU.
+    Returns the result dict on rank 0 (None elsewhere)."""
     import numpy as np
+
+    from sliceslice_rs_b200 import sharded
 
     i386 = load_i386()
     needle = args.needle.encode()
-    k = len(needle)
     S = int(args.gib * (1 << 30))
     start = rank * S
-    # haystack lengths 0..16383 from a fixed LCG (same sequence on every rank), cut from the i386 tiling
+    # haystack lengths 0..16383 from a fixed generator (same sequence on every rank), cut from the i386 tiling
     rng = np.random.default_rng(20260101)
     n_h = max(1, S // 8192 + S // 131072 + 16)  # ~6 % more than fit: the cut below always finds S
     lens = rng.integers(0, 16384, n_h, dtype=np.int64)
@@ -532,24 +554,28 @@ def many_mode(args, ss, torch, dist, world, rank, local):
     elif off[-1] < S:
         off = np.append(off, off[-1] + len(i386) - 1)
     n_h = off.size - 1
+    total_h = n_h * world
     blob_len = int(off[-1])
     src = torch.frombuffer(bytearray(i386), dtype=torch.uint8).cuda()
     blob = torch.empty(blob_len, dtype=torch.uint8, device="cuda")
     ss.fill_tiled(blob, start, src)
     hset = ss.HaystackSet.from_device(blob, torch.from_numpy(off).cuda())
     searcher = ss.DynamicB200Searcher.new(needle)
-    ring = [torch.zeros(n_h * world, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    local_flags = torch.zeros(n_h, dtype=torch.uint8, device="cuda")
+    n_words = (total_h + 31) // 32
+    ring = [torch.zeros(n_words, dtype=torch.int32, device="cuda") for _ in range(4)]
     pending = [None] * len(ring)
 
-    def step(i):
+    def step(i, s_=None):
         j = i % len(ring)
         if pending[j] is not None:
             pending[j].wait()
             pending[j] = None
-        fl = ring[j]
-        searcher.search_many_async(hset, fl[rank * n_h:(rank + 1) * n_h])
+        (s_ or searcher).search_many_async(hset, local_flags)
+        sharded.pack_flags_async(local_flags, rank * n_h, ring[j], total_h)
         if world > 1:
-            pending[j] = dist.all_reduce(fl, op=dist.ReduceOp.MAX, async_op=True)
+            pending[j] = sharded.reduce_packed_flags(ring[j], async_op=True)
+        return ring[j]
 
     def drain():
         for j, w in enumerate(pending):
@@ -563,30 +589,26 @@ def many_mode(args, ss, torch, dist, world, rank, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # parity at full size, before timing: the bench needle and a present one, against the CPU expectation
+    # parity at full size, before timing: the bench needle and present ones, every flag of every rank
+    # against the CPU expectation
     checks = {}
     for nd in (needle, b"segment", b"the", b"descriptor table"):
         s2 = ss.DynamicB200Searcher.new(nd)
-        fl = ring[0]
-        fl.zero_()
-        s2.search_many_async(hset, fl[rank * n_h:(rank + 1) * n_h])
-        if world > 1:
-            dist.all_reduce(fl, op=dist.ReduceOp.MAX)
-        got = fl.cpu().numpy()
+        words = step(0, s2)
+        drain()
+        got = sharded.unpack_flags(words.cpu(), total_h)
         exp = np.concatenate([expected_set_flags(i386, nd, r * S, off) for r in range(world)])
         assert np.array_equal(got, exp), f"many-haystack flags differ from the CPU expectation for {nd!r}"
         checks[repr(nd)] = int(exp.sum())
-    for f in ring:
-        f.zero_()
     W = max(args.warmup, 3)
     for i in range(W):
         step(i)
     drain()
     barrier()
-    K = args.steps
+    K = steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
         time.sleep(0.25)
     launches0 = ss.launch_count()
@@ -598,7 +620,7 @@ def many_mode(args, ss, torch, dist, world, rank, local):
     e1.record()
     barrier()
     launches = ss.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and with_clocks) else None
     tt = torch.tensor([e0.elapsed_time(e1), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = tt.clone()
@@ -608,46 +630,85 @@ def many_mode(args, ss, torch, dist, world, rank, local):
         ms_total, launches = float(mx[0]), int(sm[1])
     else:
         ms_total = float(tt[0])
-    assert not ring[(K - 1) % len(ring)].any().item() or checks[repr(needle)] > 0
     # a present needle on the same set: the hit path marks haystacks instead of stopping
     hot = {}
     plain = ss.HaystackSet.from_device(blob, hset.offsets, prepared=False)
     for nd in (b"segment", b"the"):
         s2 = ss.DynamicB200Searcher.new(nd)
-        fl = ring[0][rank * n_h:(rank + 1) * n_h]
         row = {}
         for label, st in (("prepared_set", hset), ("no_hints", plain)):
             for _ in range(2):
-                s2.search_many_async(st, fl)
+                s2.search_many_async(st, local_flags)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(5):
-                s2.search_many_async(st, fl)
+                s2.search_many_async(st, local_flags)
             b.record()
             torch.cuda.synchronize()
             row[label] = round(blob_len * 5 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
         hot[repr(nd)] = row
-    if rank == 0:
-        peak, peak_src = peak_hbm()
-        value = blob_len * world * K / (ms_total * 1e-3) / 1e9
-        print(json.dumps({
-            "metric": "haystack GB/s scanned (many-haystack batch)", "value": round(value, 3), "unit": UNIT,
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 5),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"many-haystack batch: {n_h} haystacks per GPU (lengths 0..16383, cut from "
-                                   f"data/i386.txt tiled to {args.gib:g} GiB per GPU), needle {args.needle!r}, "
-                                   "flags[h] = search_in(haystack h)",
-                       "haystacks_per_gpu": n_h, "blob_bytes_per_gpu": blob_len,
-                       "sharding": "haystack set partitioned across GPUs; per-haystack uint8 flags OR-ed with "
-                                   "all_reduce(MAX) per step (async, all waited for inside the timed region)",
-                       "l2": "blob >> L2 (126 MB)"},
-            "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": round(value / world, 2), "peak": peak, "unit": UNIT,
-                         "frac": round(value / world / peak, 4), "peak_source": peak_src,
-                         "note": "whole step (flag fill + scan + exchange) per GPU, not the kernel alone"},
-            "parity": {"flags_equal_cpu_expectation_for": checks},
-            "present_needle_gbs_per_gpu": hot,
-        }), flush=True)
+    if rank != 0:
+        return None
+    peak, peak_src = peak_hbm()
+    value = blob_len * world * K / (ms_total * 1e-3) / 1e9
+    return {
+        "metric": "haystack GB/s scanned (many-haystack batch)", "value": round(value, 3), "unit": UNIT,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 5),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"many-haystack batch: {n_h} haystacks per GPU (lengths 0..16383, cut from "
+                               f"data/i386.txt tiled to {args.gib:g} GiB per GPU), needle {args.needle!r}, "
+                               "flags[h] = search_in(haystack h)",
+                   "haystacks_per_gpu": n_h, "blob_bytes_per_gpu": blob_len,
+                   "sharding": "haystack set partitioned across GPUs; per step each rank bit-packs its flags into "
+                               "its bit range of one global bitmap and the bitmaps are OR-ed with all_reduce(SUM) on "
+                               f"int32 words ({n_words * 4} bytes; async, all waited for inside the timed region)",
+                   "l2": "blob >> L2 (126 MB)"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": round(value / world, 2), "peak": peak, "unit": UNIT,
+                     "frac": round(value / world / peak, 4), "peak_source": peak_src,
+                     "note": "whole step (flag fill + scan + pack + exchange) per GPU, not the kernel alone"},
+        "parity": {"flags_equal_cpu_expectation_for": checks},
+        "present_needle_gbs_per_gpu": hot,
+    }
+
+
+def many_mode(args, ss, torch, dist, world, rank, local):
+    line = many_mode_run(args, ss, torch, dist, world, rank, local, args.steps)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def concurrent_h2d_gbs(torch, devices, nbytes=1 << 30, reps=3):
+    """Pinned host->device copy bandwidth with every device of `devices` copying its own buffer at the
+    same time (one host thread per device): the PCIe ceiling of the striped host-slice call."""
+    import threading
+
+    out = {}
+    gate = threading.Barrier(len(devices))
+
+    def work(d):
+        torch.cuda.set_device(d)
+        h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        h.fill_(7)
+        t = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{d}")
+        st = torch.cuda.Stream(device=d)
+        with torch.cuda.stream(st):
+            t.copy_(h, non_blocking=True)
+        st.synchronize()
+        gate.wait()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(st):
+            for _ in range(reps):
+                t.copy_(h, non_blocking=True)
+        st.synchronize()
+        out[d] = nbytes * reps / (time.perf_counter() - t0) / 1e9
+
+    th = [threading.Thread(target=work, args=(d,)) for d in devices]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return [round(out[d], 2) for d in devices]
 
 
 def main():
@@ -659,6 +720,7 @@ def main():
         reference_arm(args)
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -670,10 +732,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")  # host-side barriers that keep the GPUs idle
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
 
@@ -703,23 +767,87 @@ def main():
     searcher = ss.DynamicB200Searcher.new(needle)
     ws = torch.zeros(32, dtype=torch.uint8, device="cuda")
     peer = None
-    if world > 1 and args.exchange == "peer":
+    if world > 1:
         from sliceslice_rs_b200.sharded import PeerExchange
 
-        peer = PeerExchange()
+        peer = PeerExchange()  # CUDA-IPC mailboxes; used by --exchange peer, the parity plants and the latency rows
+    use_peer = peer is not None and args.exchange == "peer"
     torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    one = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def search_once(exchange: str) -> int:
+        """One complete sharded search (scan + exchange), synchronous: the global first offset."""
+        if exchange == "peer" and peer is not None:
+            peer.find_async(searcher, shard, start, owned, ws, one)
+        else:
+            searcher.find_in_async(shard, one, ws, base_offset=start, start_limit=owned)
+            if world > 1:
+                dist.all_reduce(one, op=dist.ReduceOp.MIN)
+        return int(one.item())
+
+    # ---- parity with PLANTED needles, before anything is timed (SURVEY 8d C5; src/lib.rs:242-244) ----
+    needle_t = torch.tensor(list(needle), dtype=torch.uint8, device="cuda")
+
+    def plant(pos):
+        lo, hi = max(pos, start), min(pos + k, start + span)
+        if lo >= hi:
+            return None
+        saved = shard[lo - start:hi - start].clone()
+        shard[lo - start:hi - start] = needle_t[lo - pos:hi - pos]
+        return (lo - start, saved)
+
+    def unplant(tok):
+        if tok is not None:
+            shard[tok[0]:tok[0] + tok[1].numel()] = tok[1]
+
+    exchanges = ["nccl", "peer"] if world > 1 else ["single"]
+    cases = [("last_k_bytes_of_last_rank", [total - k], total - k),
+             ("rank0_and_a_later_position", [4242, (world - 1) * S + S // 2 + 99], 4242)]
+    if world > 1:
+        cases.insert(1, ("straddling_rank_boundary", [(world // 2) * S - k // 2], (world // 2) * S - k // 2))
+    parity = {"absent": {}, "planted": {}}
+    for ex in exchanges:
+        got = search_once(ex)
+        parity["absent"][ex] = {"expected": None, "got": None if got == ss.DEVICE_NONE else got}
+        assert got == ss.DEVICE_NONE, f"needle must be absent ({ex}): {got}"
+    for name, spots, expect in cases:
+        toks = [plant(p) for p in spots]
+        torch.cuda.synchronize()
+        row = {"planted_at": spots, "expected": expect}
+        for ex in exchanges:
+            got = search_once(ex)
+            row[ex] = got
+            assert got == expect, f"planted-needle parity failed: {name} via {ex}: expected {expect}, got {got}"
+        parity["planted"][name] = row
+        for t in reversed(toks):
+            unplant(t)
+        torch.cuda.synchronize()
+    got = search_once(exchanges[0])
+    assert got == ss.DEVICE_NONE, "the plants must be gone again before the timed region"
 
     # One result slot per step: consecutive searches are independent, so the 8-byte MIN-allreduce of
     # step i runs on NCCL's stream (async_op) while step i+1 already scans; every reduction is
     # waited for before the closing event of the timed region.
-    n_slots = max(args.steps, args.warmup, 3)
+    n_slots = max(args.steps, args.warmup, args.sustained_steps, 3)
     results = torch.zeros(n_slots, dtype=torch.int64, device="cuda")
     pending = []
 
     def step(i, ev_a=None, ev_b=None):
         if ev_a is not None:
             ev_a.record()
-        if peer is not None:
+        if use_peer:
             # scan + exchange in one call: the scan's last CTA stores into every rank's mailbox
             peer.find_async(searcher, shard, start, owned, ws, results[i:i + 1])
             if ev_b is not None:
@@ -736,11 +864,35 @@ def main():
             w.wait()
         pending.clear()
 
-    def barrier():
-        torch.cuda.synchronize()
+    def timed_run(K, per_step_events):
+        ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)] if per_step_events else [None] * K
+        kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)] if per_step_events else [None] * K
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        launches0 = ss.launch_count()
+        barrier()
+        e0.record()
+        for i in range(K):
+            step(i, ka[i], kb[i])
+        drain()
+        e1.record()
+        barrier()
+        launches = ss.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        assert results[:K].eq(ss.DEVICE_NONE).all().item()
+        ms_total = e0.elapsed_time(e1)
+        kern = sum(a.elapsed_time(b) for a, b in zip(ka, kb)) / K if per_step_events else 0.0
+        tt = torch.tensor([ms_total, kern, float(launches)], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            return float(mx[0]), float(mx[1]), int(sm[2]), clocks
+        return float(tt[0]), float(tt[1]), int(tt[2]), clocks
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -749,90 +901,195 @@ def main():
     assert results[: max(args.warmup, 3)].eq(ss.DEVICE_NONE).all().item(), "needle must be absent"
 
     K = args.steps
-    ka = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    kb = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    launches0 = ss.launch_count()
-    barrier()
-    e0.record()
-    for i in range(K):
-        step(i, ka[i], kb[i])
-    drain()
-    e1.record()
-    barrier()
-    launches = ss.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    assert results[:K].eq(ss.DEVICE_NONE).all().item()
-
-    ms_total = e0.elapsed_time(e1)
-    kern_ms = [a.elapsed_time(b) for a, b in zip(ka, kb)]
-    tt = torch.tensor([ms_total, sum(kern_ms) / K, float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = tt.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_total, kern_avg_ms, launches = float(mx[0]), float(mx[1]), int(sm[2])
-    else:
-        kern_avg_ms = float(tt[1])
+    ms_total, kern_avg_ms, launches, clocks = timed_run(K, True)
     value = total * K / (ms_total * 1e-3) / 1e9
     peak, peak_src = peak_hbm()
     kern_bytes = owned + k - 1 if owned else 0  # bytes one launch must examine (not found => all of them)
     achieved = kern_bytes / (kern_avg_ms * 1e-3) / 1e9
     traffic = committed_traffic()
 
+    # ---- sustained: a longer run of the same step, so the power-capped rate is on the record ----
+    sustained = None
+    if args.sustained_steps > 0:
+        ms_s, _, _, clk_s = timed_run(args.sustained_steps, False)
+        sustained = {"steps": args.sustained_steps, "ms_per_step": round(ms_s / args.sustained_steps, 5),
+                     "value": round(total * args.sustained_steps / (ms_s * 1e-3) / 1e9, 3), "unit": UNIT,
+                     "frac_of_peak_per_gpu": round(total * args.sustained_steps / (ms_s * 1e-3) / 1e9 / world / peak, 4),
+                     "clocks": clk_s}
+
+    # ---- unpipelined latency of one complete search (scan + exchange + result on the host) ----
+    latency = {}
+    for ex in exchanges:
+        for _ in range(3):
+            search_once(ex)
+        barrier()
+        ts = []
+        for _ in range(15):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            search_once(ex)
+            ts.append(time.perf_counter() - t0)
+        tl = torch.tensor([statistics.median(ts) * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        latency[ex] = round(float(tl[0]), 4)
+
+    # ---- found needles: how long until the answer, planted at 25 % / 50 % / the last k bytes ----
+    found = {}
+    for label, pos in (("at_25pct", total // 4 + 7), ("at_50pct", total // 2 + 7), ("last_k_bytes", total - k)):
+        tok = plant(pos)
+        torch.cuda.synchronize()
+        row = {"offset": pos}
+        for ex in exchanges:
+            assert search_once(ex) == pos
+            barrier()
+            ts = []
+            for _ in range(5):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                search_once(ex)
+                ts.append(time.perf_counter() - t0)
+            tl = torch.tensor([min(ts) * 1e3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            row[f"ms_{ex}"] = round(float(tl[0]), 4)
+        found[label] = row
+        unplant(tok)
+        torch.cuda.synchronize()
+    found["note"] = ("host wall clock of one synchronous search, max over ranks; the GPUs left of the match must "
+                     "finish their shards (nothing earlier exists only once they have looked), the ones to its right "
+                     "are stopped through the peer stop words (exchange 'peer') or run to the end (exchange 'nccl')")
+
     # ---- e2e: host buffer -> C ABI -> result, copies inside the timed region ----------------
     def measure_e2e():
         eg = args.e2e_gib or args.gib
-        n_host = min(int(eg * (1 << 30)), span)
-        try:
-            host = torch.empty(n_host, dtype=torch.uint8, pin_memory=True)
-        except Exception:
-            n_host = min(n_host, 1 << 30)
-            host = torch.empty(n_host, dtype=torch.uint8, pin_memory=True)
-        host.copy_(shard[:n_host])
-        torch.cuda.synchronize()
-        for _ in range(2):
-            assert searcher.find_in(host) is None
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            r = searcher.find_in(host)  # ss_b200_find_in_host: chunked H2D + scan + result read
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        assert r is None
-        td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        n_host = min(int(eg * (1 << 30)), S)
+        line = None
+        if rank == 0:
+            total_host = n_host * world
+            t0 = time.perf_counter()
+            try:
+                host = torch.empty(total_host, dtype=torch.uint8, pin_memory=True)
+            except Exception:
+                n_host = min(n_host, 1 << 30)
+                total_host = n_host * world
+                host = torch.empty(total_host, dtype=torch.uint8, pin_memory=True)
+            pin_s = time.perf_counter() - t0
+            # the same tiling as the device-resident workload, generated on the GPU piece by piece
+            tmp = torch.empty(n_host, dtype=torch.uint8, device="cuda")
+            for r in range(world):
+                ss.fill_tiled(tmp, r * n_host, src)
+                host[r * n_host:(r + 1) * n_host].copy_(tmp)
+            del tmp
+            torch.cuda.synchronize()
+            if world > 1:
+                ctx = ss.Context(devices=list(range(world)))
+                call = lambda: ctx.find_in_host(searcher, host)  # noqa: E731
+                call_name = ("ss_b200_find_in_host_multi: ONE pinned host slice striped over all GPUs by the library "
+                             "(chunk i -> GPU i mod N, a copy/scan ring per GPU), called by rank 0")
+                h2d_peak = concurrent_h2d_gbs(torch, list(range(world)))
+            else:
+                ctx = None
+                call = lambda: searcher.find_in(host)  # noqa: E731
+                call_name = "ss_b200_find_in_host (pinned host haystack, ring of 3 device buffers)"
+                h2d_peak = [round(ss.measure_h2d(1 << 30, 3), 2)]
+            # positive parity first: the needle planted in the host slice (restored afterwards)
+            hv = host.numpy()
+            e2e_parity = {}
+            nd_np = np.frombuffer(needle, np.uint8)
+            for label, pos in (("last_k_bytes", total_host - k), ("middle", (total_host // 2) - k // 2), ("early", 4242)):
+                saved = hv[pos:pos + k].copy()
+                hv[pos:pos + k] = nd_np
+                got = call()
+                hv[pos:pos + k] = saved
+                e2e_parity[label] = {"expected": pos, "got": got}
+                assert got == pos, f"e2e parity: planted at {pos}, got {got}"
+            for _ in range(2):
+                assert call() is None
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                r_ = call()
+            dt = time.perf_counter() - t0
+            assert r_ is None
+            if ctx is not None:
+                st = ctx.last_host_stats()
+                h2d, chunks = st["h2d_bytes"], st["chunks"]
+            else:
+                chunk = 64 << 20
+                chunks = max(1, -(-(n_host - k + 1) // chunk))
+                h2d = n_host + (chunks - 1) * (k - 1)
+            val = total_host * args.e2e_steps / dt / 1e9
+            line = {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(8 * chunks), "host_bytes": total_host, "host_bytes_per_gpu": n_host,
+                    "steps": args.e2e_steps, "pin_seconds": round(pin_s, 2),
+                    "timer": "host wall clock around the synchronous C-ABI call on rank 0",
+                    "call": call_name, "parity": e2e_parity,
+                    "roofline": {"bound": "pcie", "achieved": round(val, 2), "peak": round(sum(h2d_peak), 2),
+                                 "unit": UNIT, "frac": round(val / sum(h2d_peak), 4),
+                                 "peak_source": "pinned cudaMemcpyAsync host->device, 1 GiB per device, all devices "
+                                                "copying at once, measured in this run",
+                                 "per_device_peak": h2d_peak}}
+            if world == 1:
+                # the other data paths of the same call, for the record: pinned input read in place over PCIe,
+                # and an ordinary (pageable) buffer staged through the pinned ring by the copy pool
+                modes = {}
+                for mode, nm in ((2, "in_place_ldg"), (3, "in_place_tma")):
+                    ss.set_host_path(mode, 0, -1)
+                    sub = host[:min(n_host, 2 << 30)]
+                    assert searcher.find_in(sub) is None
+                    t0 = time.perf_counter()
+                    for _ in range(2):
+                        searcher.find_in(sub)
+                    modes[nm] = round(sub.numel() * 2 / (time.perf_counter() - t0) / 1e9, 3)
+                ss.set_host_path(0, 0, -1)
+                sizes = {}
+                for mib in (1, 16, 256):
+                    sub = host[:mib << 20]
+                    row = {}
+                    for mode, nm in ((1, "dma_ring"), (2, "in_place_ldg")):
+                        ss.set_host_path(mode, 0, -1)
+                        assert searcher.find_in(sub) is None
+                        reps = 30 if mib <= 16 else 5
+                        t0 = time.perf_counter()
+                        for _ in range(reps):
+                            searcher.find_in(sub)
+                        row[nm] = round(sub.numel() * reps / (time.perf_counter() - t0) / 1e9, 3)
+                    sizes[f"{mib}MiB"] = row
+                ss.set_host_path(0, 0, -1)
+                line["other_data_paths_gbs"] = modes
+                line["by_slice_size_gbs"] = sizes
+                n_pg = min(n_host, 2 << 30)
+                pageable = np.empty(n_pg, np.uint8)
+                pageable[:] = hv[:n_pg]
+                assert searcher.find_in(pageable) is None
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    searcher.find_in(pageable)
+                line["pageable_host_buffer_gbs"] = round(n_pg * 3 / (time.perf_counter() - t0) / 1e9, 3)
+                del pageable
+            if ctx is not None:
+                ctx.close()
+            del host
+        host_barrier()
         if world > 1:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        dt = float(td[0])
-        chunk = int(os.environ.get("SS_B200_HOST_CHUNK_MIB", "64")) << 20
-        n_chunks = max(1, -(-(n_host - k + 1) // chunk))
-        e2e_line = {"value": round(n_host * world * args.e2e_steps / dt / 1e9, 3), "unit": UNIT,
-               "h2d_bytes_per_step": (n_host + (n_chunks - 1) * (k - 1)) * world,
-               "d2h_bytes_per_step": 8 * n_chunks * world,
-               "host_bytes_per_gpu": n_host, "steps": args.e2e_steps,
-               "timer": "host wall clock around the synchronous C-ABI call, max over ranks",
-               "call": "ss_b200_find_in_host (pinned host haystack, 64 MiB chunks, 3 staging buffers)"}
-        if world == 1:
-            # the same call on an ordinary (pageable) host buffer, what a caller's &[u8] normally is:
-            # staged through pinned buffers by the library's copy pool
-            import numpy as np
-
-            n_pg = min(n_host, 2 << 30)
-            pageable = np.empty(n_pg, np.uint8)
-            pageable[:] = host[:n_pg].numpy()
-            assert searcher.find_in(pageable) is None
+            # for comparison: one process per GPU, each searching its own pinned slice at the same time
+            # (round 1's e2e); what a host gets WITHOUT the context call
+            n_pp = min(n_host, 2 << 30)
+            hp = torch.empty(n_pp, dtype=torch.uint8, pin_memory=True)
+            hp.copy_(shard[:n_pp])
+            torch.cuda.synchronize()
+            assert searcher.find_in(hp) is None
+            host_barrier()
             t0 = time.perf_counter()
             for _ in range(3):
-                searcher.find_in(pageable)
-            e2e_line["pageable_host_buffer_gbs"] = round(n_pg * 3 / (time.perf_counter() - t0) / 1e9, 3)
-            del pageable
-        del host
-        return e2e_line
+                searcher.find_in(hp)
+            dt = time.perf_counter() - t0
+            td = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            if rank == 0 and line is not None:
+                line["one_process_per_gpu_gbs"] = round(n_pp * world * 3 / float(td[0]) / 1e9, 3)
+            del hp
+        return line
 
     e2e = None
     if not args.no_e2e:
@@ -840,17 +1097,30 @@ def main():
             e2e = measure_e2e()
         except Exception as e:  # noqa: BLE001
             e2e = {"error": f"{type(e).__name__}: {e}"}
+            host_barrier()
 
     # context blocks: a failure here must not cost the headline line its numbers
-    extras = None
-    if rank == 0 and world == 1 and not args.no_extras:
+    extras = {}
+    if not args.no_extras:
+        if rank == 0 and world == 1:
+            try:
+                extras = extras_single_gpu(ss, torch, i386, shard, args)
+            except Exception as e:  # noqa: BLE001
+                extras = {"error": f"{type(e).__name__}: {e}"}
+        del shard
+        torch.cuda.empty_cache()
+        # the north-star's batched many-haystack mode at this N (its own full-size parity check inside)
         try:
-            extras = extras_single_gpu(ss, torch, i386, shard, args)
+            mm = many_mode_run(args, ss, torch, dist, world, rank, local, min(args.steps, 40), with_clocks=False)
+            if rank == 0:
+                extras["many_haystack_mode"] = {kk: mm[kk] for kk in ("value", "unit", "ms_per_step", "steps", "config",
+                                                                      "parity", "present_needle_gbs_per_gpu",
+                                                                      "gpu_launches")}
         except Exception as e:  # noqa: BLE001
-            extras = {"error": f"{type(e).__name__}: {e}"}
+            if rank == 0:
+                extras["many_haystack_mode"] = {"error": f"{type(e).__name__}: {e}"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        del shard
         torch.cuda.empty_cache()
         try:
             cpu = cpu_baseline(i386, needle, args.cpu_sample_gib)
@@ -858,21 +1128,19 @@ def main():
             cpu = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
+        cfg = workload_config(args, world)
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / K, 5), "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {
-                "workload": f"i386 long-haystack: data/i386.txt tiled to {args.gib:g} GiB per GPU, needle "
-                            f"{args.needle!r} (absent => full scan), DynamicAvx2Searcher::new semantics",
-                "haystack_bytes_per_gpu": S, "needle_len": k, "position": k - 1,
+            "config": cfg,
+            "implementation": {
                 "sharding": ("single GPU" if world == 1 else
                              "contiguous start-position ranges + k-1 byte right halo; " +
                              ("first offsets MIN-reduced through peer mailboxes: 8-byte NVLink stores fused into the "
-                              "scan epilogue + a one-warp min kernel (no collective call)" if peer is not None else
+                              "scan epilogue + a one-warp min kernel (no collective call)" if use_peer else
                               "NCCL all_reduce(MIN) of the 8-byte first offset per step, overlapped with the next "
                               "step's scan (async_op, all waited for inside the timed region)")),
-                "l2": "haystack >> L2 (126 MB): every step streams from HBM, no flush needed",
                 "kernel_variant": {0: "auto", 1: "ldg", 2: "tma"}[args.variant],
             },
             "gpu_launches": launches,
@@ -892,11 +1160,16 @@ def main():
                          "traffic_source": ((traffic or {}).get("source")
                                             if abs(kern_bytes - (8 << 30)) < (1 << 20) else None)},
             "cpu_baseline": cpu,
-            "parity": "needle absent on every step (result == DEVICE_NONE on all ranks); see tests/ -m gpu",
+            "parity": parity,
+            "sustained": sustained,
+            "single_search_latency_ms": latency,
+            "found_needle": found,
         }
         if extras:
             line["extras"] = extras
         print(json.dumps(line), flush=True)
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -191,7 +191,7 @@ __device__ __noinline__ void multi_verify(const MultiArgs &m, const MultiNeedle 
     fc.bs = 8u * (d.pos & 3u);
     uint32_t z[4];
     const uint8_t *nd = m.nblob + d.off;
-    if (!exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, d.k, [&](uint32_t j) { return (uint32_t)__ldg(nd + j); }, z))
+    if (!exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, d.k, [&](uint32_t j) { return 0x01010101u * (uint32_t)__ldg(nd + j); }, z))
         return;
     const long long p0 = (long long)(chunk * 16ull) - (long long)m.head;
 #pragma unroll

@@ -140,7 +140,7 @@ extern "C" int ss_b200_set_launch_pdl(int on)
 }
 extern "C" int ss_b200_set_host_path(int mode, int chunk_mib, int copy_threads)
 {
-    if (mode < 0 || mode > 2 || chunk_mib < 0 || chunk_mib > 4096 || copy_threads < -1 || copy_threads > 256)
+    if (mode < 0 || mode > 3 || chunk_mib < 0 || chunk_mib > 4096 || copy_threads < -1 || copy_threads > 256)
         return SS_B200_E_ARG;
     g_tuning.host_mode = mode;
     g_tuning.host_chunk_mib = chunk_mib;
@@ -449,6 +449,8 @@ int ss_capi_build_args(const ss_b200_searcher *s, const void *dptr, size_t len, 
     a.f4 = 0x01010101u * f;
     a.l4 = 0x01010101u * l;
     memcpy(a.needle_inline, s->needle.data(), k < SS_INLINE_NEEDLE_MAX ? k : SS_INLINE_NEEDLE_MAX);
+    for (size_t j = 1; j < 17 && j < k; j++)
+        a.needle4[j] = 0x01010101u * s->needle[j];
     if (k > SS_INLINE_NEEDLE_MAX) {
         int rc = needle_on_device(s, dev, &a.needle_g);
         if (rc != SS_B200_OK)
@@ -458,9 +460,8 @@ int ss_capi_build_args(const ss_b200_searcher *s, const void *dptr, size_t len, 
     return SS_B200_OK;
 }
 
-extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len,
-                                            uint64_t base_offset, size_t start_limit, void *workspace,
-                                            uint64_t *d_result, void *stream)
+int ss_capi_find_async(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base_offset,
+                       size_t start_limit, void *workspace, uint64_t *d_result, void *stream, const SsStopSpec *stop)
 {
     if (!s || !d_result || !workspace || (len && !dptr))
         return SS_B200_E_ARG;
@@ -489,8 +490,26 @@ extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const voi
         return rc;
     a.ws = (SsWorkspace *)workspace;
     a.out = (unsigned long long *)d_result;
+    if (stop)
+        ss_capi_apply_stop(a, *stop);
     SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, st));
     return SS_B200_OK;
+}
+
+void ss_capi_apply_stop(ScanArgs &a, const SsStopSpec &stop)
+{
+    a.stop_word = stop.stop_word;
+    a.stop_seq = stop.seq;
+    a.n_stop_peers = stop.n_peers < SS_MAX_PEERS ? stop.n_peers : SS_MAX_PEERS;
+    for (uint32_t p = 0; p < a.n_stop_peers; p++)
+        a.stop_peer[p] = stop.peers[p];
+}
+
+extern "C" int ss_b200_find_in_device_async(const ss_b200_searcher *s, const void *dptr, size_t len,
+                                            uint64_t base_offset, size_t start_limit, void *workspace,
+                                            uint64_t *d_result, void *stream)
+{
+    return ss_capi_find_async(s, dptr, len, base_offset, start_limit, workspace, d_result, stream, nullptr);
 }
 
 // Many-haystack mode: one needle against a device-resident set of haystacks in one pass.

@@ -458,14 +458,25 @@ extern "C" int ss_b200_find_sharded(ss_b200_ctx *c, const ss_b200_searcher *s, c
         }
         lane->slot->value = SS_RESULT_PENDING;
         uint64_t *slot = (uint64_t *)&lane->slot_dev->value;
+        // cross-GPU early exit (the peer exchange carries its own stop words in the mailboxes): shard d
+        // polls the stop word in its lane's workspace block and, on its first match, stores the search's
+        // sequence number into the stop words of the shards to its right
+        SsStopSpec stop;
+        if (c->peer_access && n > 1) {
+            stop.stop_word = (const unsigned long long *)((const uint8_t *)lane->ws + 32);
+            stop.seq = c->seq;
+            for (int r = d + 1; r < n; r++)
+                stop.peers[stop.n_peers++] = (unsigned long long *)((uint8_t *)c->lane_ptrs[r]->ws + 32);
+        }
+        const SsStopSpec *sp = stop.stop_word ? &stop : nullptr;
         if (ex == SS_B200_EXCHANGE_PEER) {
             rc = ss_b200_find_in_device_exchange_async(s, p.dptr, p.span, p.start, p.owned, lane->ws,
                                                        c->mailbox.data(), n, d, c->seq, slot, lane->stream);
         } else if (ex == SS_B200_EXCHANGE_NCCL) {
-            rc = ss_b200_find_in_device_async(s, p.dptr, p.span, p.start, p.owned, lane->ws, (uint64_t *)c->red[d],
-                                              lane->stream);
+            rc = ss_capi_find_async(s, p.dptr, p.span, p.start, p.owned, lane->ws, (uint64_t *)c->red[d],
+                                    lane->stream, sp);
         } else {
-            rc = ss_b200_find_in_device_async(s, p.dptr, p.span, p.start, p.owned, lane->ws, slot, lane->stream);
+            rc = ss_capi_find_async(s, p.dptr, p.span, p.start, p.owned, lane->ws, slot, lane->stream, sp);
         }
     }
     if (rc == SS_B200_OK && ex == SS_B200_EXCHANGE_NCCL) {

@@ -8,6 +8,8 @@
 // Peer mailbox exchange: the MIN over ranks of the first offsets without a collective call.
 // Mailbox layout (per rank, plain cudaMalloc memory shared through CUDA IPC):
 //   u64 slot[SS_MAILBOX_DEPTH][world]; slot[seq % 4][r] = result of rank r for search `seq`
+//   u64 stop;  the sequence number of a search for which a rank to the LEFT has already matched: this
+//              rank's scan polls it and stops (cross-GPU early exit, ScanArgs::stop_word)
 // Search `seq` on rank r: the scan's last CTA stores its result into slot[seq%4][r] of EVERY rank's
 // mailbox (scan_finish); mailbox_min_kernel, enqueued right behind the scan, waits until the `world`
 // slots of its own mailbox are filled, writes their minimum and empties them again.  A rank can run
@@ -55,7 +57,7 @@ extern "C" int ss_b200_mailbox_create(int world, void **d_mailbox)
     if (!d_mailbox || world < 1 || world > SS_MAX_PEERS)
         return SS_B200_E_ARG;
     unsigned long long *mb = nullptr;
-    const int n = SS_MAILBOX_DEPTH * world;
+    const int n = SS_MAILBOX_DEPTH * world + 2; // + the stop word (all-ones: no search has that number)
     SS_CUDA(cudaMalloc((void **)&mb, (size_t)n * 8));
     mailbox_fill_kernel<<<1, 64>>>(mb, n);
     ss_host_count_launch(1);
@@ -132,6 +134,14 @@ extern "C" int ss_b200_find_in_device_exchange_async(const ss_b200_searcher *s, 
         a.n_peers = (uint32_t)world;
         for (int p = 0; p < world; p++)
             a.peer_slot[p] = (unsigned long long *)mailboxes[p] + row + rank;
+        // cross-GPU early exit: poll the own stop word, tell the ranks to the right about the first match
+        SsStopSpec stop;
+        const size_t stop_index = (size_t)SS_MAILBOX_DEPTH * (size_t)world;
+        stop.stop_word = (const unsigned long long *)mailboxes[rank] + stop_index;
+        stop.seq = seq;
+        for (int p = rank + 1; p < world; p++)
+            stop.peers[stop.n_peers++] = (unsigned long long *)mailboxes[p] + stop_index;
+        ss_capi_apply_stop(a, stop);
         SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, st));
     }
     mailbox_min_kernel<<<1, 32, 0, st>>>((unsigned long long *)mailboxes[rank] + row, world,

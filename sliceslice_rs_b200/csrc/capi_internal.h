@@ -117,6 +117,19 @@ int ss_capi_wait_slot(volatile unsigned long long *word, unsigned long long pend
 // host slices up to this size are searched in place from a mapped pinned copy (host_engine.cu)
 #define SS_SMALL_HOST_MAX (32u << 10)
 
+// cross-GPU early exit of a sharded first-match search (ScanArgs::stop_word): this shard polls
+// `stop_word`, and on its first match stores `seq` into the stop words of the shards to its right
+struct SsStopSpec {
+    const unsigned long long *stop_word = nullptr;
+    unsigned long long seq = 0;
+    unsigned long long *peers[SS_MAX_PEERS] = {};
+    uint32_t n_peers = 0;
+};
+void ss_capi_apply_stop(ScanArgs &a, const SsStopSpec &stop);
+// ss_b200_find_in_device_async with an optional stop spec
+int ss_capi_find_async(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base_offset,
+                       size_t start_limit, void *workspace, uint64_t *d_result, void *stream, const SsStopSpec *stop);
+
 // kernel arguments for one scan of (dptr, len) with this searcher (k >= 1, len >= k)
 int ss_capi_build_args(const ss_b200_searcher *s, const void *dptr, size_t len, uint64_t base, size_t start_limit,
                        int dev, ScanArgs &a);

@@ -80,7 +80,8 @@ __device__ __forceinline__ FilterConsts load_filter_consts(const ScanArgs &a)
 // Returns true when the early-exit test says this CTA can stop.
 template <int WS, bool BSZ, bool QZ, bool K1, int XK, int U, bool CLAMP>
 __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restrict__ chunks, unsigned long long cw,
-                                         int lane, const FilterConsts &fc, AdaptiveFilter &af, uint32_t &occ)
+                                         int lane, const FilterConsts &fc, AdaptiveFilter &af, uint32_t &occ,
+                                         bool &many_hot)
 {
     // early exit: nothing at or right of this warp's first position can beat the current best
     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
@@ -130,7 +131,7 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
         // soon as any lane's reading says so; the vote keeps the decision warp-uniform whatever each
         // lane's load returned
         const long long first_pos = (long long)(cw * 16ull) - (long long)a.head;
-        if (__any_sync(0xFFFFFFFFu, key != 0 && first_pos > (long long)~key))
+        if (__any_sync(0xFFFFFFFFu, (key != 0 && first_pos > (long long)~key) || peer_stop_requested(a)))
             return true;
     }
     uint32_t fl[U];
@@ -147,21 +148,27 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
     if (slow) {
         // many-haystack mode over a prepared set: a step that lies inside one already-flagged haystack
         // has nothing left to decide
-        if (a.seg_hint != nullptr &&
-            many_step_covered(a, (long long)(cw * 16ull) - (long long)a.head,
-                              (long long)((cw + U * 32) * 16ull) - (long long)a.head - 1))
+        // (only while this warp's previous hit path did flag something: an absent needle never pays
+        // for the lookup)
+        if (many_hot && many_step_covered(a, (long long)(cw * 16ull) - (long long)a.head,
+                                          (long long)((cw + U * 32) * 16ull) - (long long)a.head - 1))
             return false;
         if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
             for (int u = 0; u < U; u++)
                 nx[u] = load_nx(u);
         }
+        uint32_t got = 0;
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const unsigned long long c = c0 + u * 32;
             if (fl[u] && (!CLAMP || c < a.n_chunks))
-                occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
+                got += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
         }
+        if (a.seg_hint != nullptr)
+            many_hot = __any_sync(0xFFFFFFFFu, got != 0); // launch-uniform branch
+        else
+            occ += got;
     }
     return false;
 }
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
     const FilterConsts fc = load_filter_consts(a);
     AdaptiveFilter af;
     uint32_t occ = 0; // count mode: occurrences seen by this thread
+    bool many_hot = false; // many-haystack mode: this warp's last hit path flagged a haystack
 
     // Programmatic dependent launch (scan_long.cu launches this variant with programmatic stream
     // serialisation): let the next kernel of the stream start launching now, and touch no global memory
@@ -202,11 +210,11 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
         bool stop;
         if (tile < n_interior) {
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af, occ);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af, occ, many_hot);
         } else {
             if (cw >= a.n_chunks)
                 continue; // this warp's run holds no start position (warp-uniform)
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af, occ);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af, occ, many_hot);
         }
         if (stop)
             break; // every later tile of this CTA is further right still
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
                 if (go) {
                     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
                     const long long first_pos = (long long)(tile * (unsigned long long)TILE) - (long long)a.head;
-                    if (key && first_pos > (long long)~key)
+                    if ((key && first_pos > (long long)~key) || peer_stop_requested(a))
                         go = false;
                 }
                 if (!go) {
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
         const FilterConsts fc = load_filter_consts(a);
         AdaptiveFilter af;
         uint32_t occ = 0; // count mode: occurrences seen by this thread
+        bool many_hot = false; // many-haystack mode: this warp's last hit path flagged a haystack
         const uint32_t qb = a.q * 16u;
         int s = 0;
         uint32_t ph = 0;
@@ -342,21 +351,27 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
                     // many-haystack mode over a prepared set: a step that lies inside one already-flagged
                     // haystack has nothing left to decide (warp-uniform)
                     const unsigned long long sc0 = tile_c0 + (unsigned long long)(lc0 - lane);
-                    if (a.seg_hint != nullptr &&
-                        many_step_covered(a, (long long)(sc0 * 16ull) - (long long)a.head,
-                                          (long long)((sc0 + 32 * U) * 16ull) - (long long)a.head - 1))
+                    // (only while this warp's previous hit path did flag something: an absent needle never
+                    // pays for the lookup)
+                    if (many_hot && many_step_covered(a, (long long)(sc0 * 16ull) - (long long)a.head,
+                                                      (long long)((sc0 + 32 * U) * 16ull) - (long long)a.head - 1))
                         continue;
                     if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
                         for (int u = 0; u < U; u++)
                             nx[u] = lds16(st + (lc0 + u * 32) * 16u + 16u);
                     }
+                    uint32_t got = 0;
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const unsigned long long c = tile_c0 + lc0 + u * 32;
                         if (fl[u] && c < a.n_chunks)
-                            occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
+                            got += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
                     }
+                    if (a.seg_hint != nullptr)
+                        many_hot = __any_sync(0xFFFFFFFFu, got != 0); // launch-uniform branch
+                    else
+                        occ += got;
                 }
             }
             if (XK != 0)

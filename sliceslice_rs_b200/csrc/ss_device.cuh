@@ -57,7 +57,15 @@ struct ScanArgs {
     // [seq % 4][rank] of every rank's mailbox (peer memory over NVLink), fused into the scan epilogue
     unsigned long long *peer_slot[SS_MAX_PEERS];
     uint32_t n_peers;
-    uint32_t pad_peers;
+    // cross-GPU early exit of a sharded first-match search (n_stop_peers == 0 and stop_word == nullptr:
+    // off).  The first verified match on this GPU stores `stop_seq` into the stop word of every shard to
+    // its RIGHT (peer memory): whatever those find is larger than this match, so they may stop -- the
+    // reference's early return (src/lib.rs:242-244) across devices.  This GPU polls its own stop word
+    // where it polls `key`; a value other than the current search's sequence number is stale and ignored.
+    uint32_t n_stop_peers;
+    unsigned long long *stop_peer[SS_MAX_PEERS];
+    const unsigned long long *stop_word;
+    unsigned long long stop_seq;
     // many-haystack mode (nullptr otherwise): hay is the concatenation of n_seg haystacks, haystack h
     // = bytes [seg_off[h], seg_off[h+1]) with seg_off[0] == 0; seg_flags[h] <- 1 when it contains the needle
     const unsigned long long *seg_off;
@@ -70,6 +78,9 @@ struct ScanArgs {
     // count mode (nullptr otherwise): incremented once per occurrence
     unsigned long long *count;
     uint8_t needle_inline[SS_INLINE_NEEDLE_MAX]; // first min(k, 64) needle bytes
+    // needle bytes 1..16 splatted over a word each (index 0 unused): the register verify of the hit path
+    // takes them straight from the constant bank as instruction operands
+    uint32_t needle4[17];
 };
 
 __device__ __forceinline__ uint4 ldg16(const uint4 *p)
@@ -87,6 +98,16 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 }
 
 #include "ss_filter.cuh"
+
+// Has a shard to the left already matched (see ScanArgs::stop_word)?  Launch-uniform branch on the pointer.
+__device__ __forceinline__ bool peer_stop_requested(const ScanArgs &a)
+{
+    if (a.stop_word == nullptr)
+        return false;
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.stop_word) : "memory");
+    return v == a.stop_seq;
+}
 
 // Per-warp, per-tile switch between the plain two-anchor filter and the one with extra anchors.
 // The plain filter is cheapest when candidates are rare (random bytes); on natural text a common
@@ -236,35 +257,21 @@ static __device__ __noinline__ bool many_step_covered(const ScanArgs &a, long lo
     return ld_relaxed_u8(a.seg_flags + h) != 0;
 }
 
-#define SS_MODE_FIND 0  // first match: leftmost offset, early exit
-#define SS_MODE_COUNT 1 // every occurrence counted, no early exit
-#define SS_MODE_MANY 2  // many-haystack mode: flag the haystack holding the match, no early exit
-
-// Hit path for one chunk whose SWAR flag fired -- the ctz loop + memcmp of src/lib.rs:216-248, done
-// without touching memory: the lane already holds the 32 haystack bytes [16c, 16c+32) in registers,
-// which cover needle bytes 0..16 of every start position of the chunk (exact_alive).  Natural-text false
-// candidates leave after a few needle bytes.  Survivors (17 bytes equal) of longer needles finish from
-// global memory.
-// Returns the number of occurrences counted (count mode only; 0 in every other mode): the caller keeps
-// the running total in a register and adds it to *a.count once per warp at the end of the kernel
-// (count_flush) -- one atomic per occurrence on a single address would serialise in L2.
-template <int WS, bool BSZ, bool K1, int MODE>
-__device__ __noinline__ uint32_t verify_chunk_mode(const ScanArgs &a, uint4 av, uint4 nx, uint4 lo, uint4 hi,
-                                                   unsigned long long chunk)
+// What is left of the hit path once a chunk holds a position whose first min(k, 17) bytes equal the
+// needle's (z: 0x80 in the byte of each such start position) -- rare unless the needle really occurs:
+// range check, the rest of a long needle from memory, and the action of the mode.
+//   first match  leftmost offset, early exit: CTA-level best first, the global word only when this lane
+//                lowered it, the stop words of the shards to the right on the GPU's first match
+//   count        every occurrence (overlapping ones included), no early exit; returns the number counted
+//                (the caller keeps the running total in a register, count_flush adds it once per warp)
+//   many         the blob is a concatenation of haystacks; flag the haystack that wholly contains the
+//                match, no early exit
+static __device__ __noinline__ uint32_t hit_tail(const ScanArgs &a, uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3,
+                                                 unsigned long long chunk)
 {
-    FilterConsts fc;
-    fc.f4 = a.f4;
-    fc.l4 = a.l4;
-    fc.bs = a.bs;
-    uint32_t z[4];
-    if (!exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, a.k, [&](uint32_t j) { return (uint32_t)a.needle_inline[j]; }, z))
-        return 0;
+    const uint32_t z[4] = {z0, z1, z2, z3};
     const long long p0 = (long long)(chunk * 16ull) - (long long)a.head; // position of byte 0 of the chunk
-    if (MODE == SS_MODE_COUNT && (K1 || a.k <= 17u) && p0 >= 0 && (unsigned long long)p0 + 16ull <= a.end) {
-        // every surviving bit is an occurrence (the register window covered the whole needle) and every
-        // position of the chunk is in range: no bit loop
-        return __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
-    }
+    const bool one_byte = a.k == 1u;
     uint32_t occ = 0;
     unsigned long long flagged_until = 0; // many mode: positions below this lie in a haystack flagged just now
 #pragma unroll
@@ -276,25 +283,30 @@ __device__ __noinline__ uint32_t verify_chunk_mode(const ScanArgs &a, uint4 av, 
             const long long i = p0 + 4 * j + (bit >> 3);
             if (i < 0 || (unsigned long long)i >= a.end)
                 continue;
-            if (MODE == SS_MODE_MANY && (unsigned long long)i < flagged_until)
+            if (a.seg_off != nullptr && (unsigned long long)i < flagged_until)
                 continue;
-            if (K1 || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
-                if (MODE == SS_MODE_COUNT) {
-                    occ++; // every occurrence (overlapping ones included), no early exit
+            if (one_byte || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
+                if (a.count != nullptr) {
+                    occ++;
                     continue;
                 }
-                if (MODE == SS_MODE_MANY) {
-                    // the blob is a concatenation of haystacks; a match counts for haystack h iff it lies
-                    // entirely inside [seg_off[h], seg_off[h+1]).  No early exit.
+                if (a.seg_off != nullptr) {
                     flagged_until = segment_hit(a, (unsigned long long)i);
+                    occ = 1; // "this step flagged something": switches the covered-step check on (scan_long.cuh)
                     continue;
                 }
-                // first-match mode: CTA-level best first, the global word only when this lane lowered it.
                 // No fence: `key` is only ever touched with atomics and relaxed loads, and the acq_rel
                 // ticket of scan_finish (behind a CTA barrier) orders every atomicMax before the final read.
                 const unsigned long long old = atomicMin(&ss_cta_best, (unsigned long long)i);
-                if ((unsigned long long)i < old)
-                    atomicMax(&a.ws->key, ~(unsigned long long)i);
+                if ((unsigned long long)i < old) {
+                    const unsigned long long prev = atomicMax(&a.ws->key, ~(unsigned long long)i);
+                    if (prev == 0ull) {
+                        // first match on this GPU: the shards to the right can stop (8-byte NVLink stores)
+                        for (uint32_t p = 0; p < a.n_stop_peers; p++)
+                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.stop_peer[p]), "l"(a.stop_seq)
+                                         : "memory");
+                    }
+                }
                 return 0; // ascending order: later positions of this chunk cannot be smaller
             }
         }
@@ -302,19 +314,33 @@ __device__ __noinline__ uint32_t verify_chunk_mode(const ScanArgs &a, uint4 av, 
     return occ;
 }
 
-// Mode dispatch (launch-uniform): one specialised hit path per mode.
+// Hit path for one chunk whose SWAR flag fired -- the ctz loop + memcmp of src/lib.rs:216-248, done
+// without touching memory: the lane already holds the 32 haystack bytes [16c, 16c+32) in registers,
+// which cover needle bytes 0..16 of every start position of the chunk (exact_alive; inlined, needle
+// bytes as constant-bank operands).  The false candidates of natural text leave after one needle byte.
+// Count mode counts the survivors of an interior chunk with four popcounts; everything else that
+// survives goes through hit_tail.  Returns occurrences counted (count mode), 1 if a haystack was flagged
+// (many mode), else 0.
 template <int WS, bool BSZ, bool K1>
 __device__ __forceinline__ uint32_t verify_chunk(const ScanArgs &a, const uint4 &av, const uint4 &nx, const uint4 &lo,
                                                  const uint4 &hi, unsigned long long chunk)
 {
-    if (a.count)
-        return verify_chunk_mode<WS, BSZ, K1, SS_MODE_COUNT>(a, av, nx, lo, hi, chunk);
-    if (a.seg_off) {
-        verify_chunk_mode<WS, BSZ, K1, SS_MODE_MANY>(a, av, nx, lo, hi, chunk);
+    FilterConsts fc;
+    fc.f4 = a.f4;
+    fc.l4 = a.l4;
+    fc.bs = a.bs;
+    uint32_t z[4];
+    if (!exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, a.k, [&](uint32_t j) { return a.needle4[j]; }, z))
         return 0;
+    if (a.count != nullptr && (K1 || a.k <= 17u)) {
+        const long long p0 = (long long)(chunk * 16ull) - (long long)a.head;
+        if (p0 >= 0 && (unsigned long long)p0 + 16ull <= a.end) {
+            // every surviving bit is an occurrence (the register window covered the whole needle) and
+            // every position of the chunk is in range: no bit loop
+            return __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
+        }
     }
-    verify_chunk_mode<WS, BSZ, K1, SS_MODE_FIND>(a, av, nx, lo, hi, chunk);
-    return 0;
+    return hit_tail(a, z[0], z[1], z[2], z[3], chunk);
 }
 
 // Count mode epilogue: add the warp's occurrences to *a.count with one atomic.  Called by whole,

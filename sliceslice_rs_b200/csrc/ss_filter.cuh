@@ -101,11 +101,11 @@ SS_UNROLL
 // zero-byte test at the end.  This is the analogue of the reference's constant-length memcmp arms
 // (src/lib.rs:222-241) for all 16 positions at once.  z[t] receives 0x80 in the byte of every start
 // position whose first min(k, 17) bytes equal the needle's; returns false when there is none (checked
-// every fourth needle byte, so false candidates of natural text leave early).
-// `needle_at(j)` yields needle byte j.
-template <int WS, bool BSZ, bool K1, class NeedleAt>
+// after needle bytes 1, 2, 4, 8 and 12, so the false candidates of natural text leave after one byte).
+// `needle4_at(j)` yields needle byte j splatted over the four bytes of a word.
+template <int WS, bool BSZ, bool K1, class Needle4At>
 SS_HD bool exact_alive(const uint4 &av, const uint4 &nx, const uint4 &lo, const uint4 &hi, const FilterConsts &fc,
-                       uint32_t k, NeedleAt needle_at, uint32_t (&z)[4])
+                       uint32_t k, Needle4At needle4_at, uint32_t (&z)[4])
 {
     const uint32_t w[8] = {av.x, av.y, av.z, av.w, nx.x, nx.y, nx.z, nx.w};
     uint32_t acc[4];
@@ -118,14 +118,14 @@ SS_UNROLL
         for (uint32_t j = 1; j <= 16u; j++) {
             if (j > jmax)
                 break;
-            const uint32_t n4 = 0x01010101u * needle_at(j);
+            const uint32_t n4 = needle4_at(j);
             const uint32_t wo = j >> 2, sh = 8u * (j & 3u); // window shifted by j bytes = wo words + sh bits
 SS_UNROLL
             for (uint32_t t = 0; t < 4; t++) {
                 const uint32_t x = sh ? ss_funnel_r(w[t + wo], w[t + wo + 1], sh) : w[t + wo];
                 acc[t] |= x ^ n4;
             }
-            if ((j & 3u) == 0u && j < jmax) {
+            if ((j == 1u || j == 2u || j == 4u || j == 8u || j == 12u) && j < jmax) {
                 const uint32_t any = (swar_zero_term(acc[0]) | swar_zero_term(acc[1]) | swar_zero_term(acc[2]) |
                                       swar_zero_term(acc[3])) & 0x80808080u;
                 if (!any)

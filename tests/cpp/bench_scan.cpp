@@ -2,7 +2,7 @@
 // also the A/B harness for kernel changes: point LD_LIBRARY_PATH at another build of the library).
 //   g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include tests/cpp/bench_scan.cpp \
 //       -Lsliceslice_rs_b200 -lsliceslice_b200 -L/usr/local/cuda/lib64 -lcudart -o bench_scan
-//   bench_scan <i386.txt> [GiB = 8] [steps = 100] [needle = ipsum]
+//   bench_scan <i386.txt> [GiB = 8] [steps = 100] [needle = ipsum] [mode = find | count]
 #include "sliceslice_b200.h"
 
 #include <cuda_runtime.h>
@@ -30,6 +30,7 @@ int main(int argc, char **argv)
     const double gib = argc > 2 ? atof(argv[2]) : 8.0;
     const int steps = argc > 3 ? atoi(argv[3]) : 100;
     const std::string needle = argc > 4 ? argv[4] : "ipsum";
+    const bool count_mode = argc > 5 && std::string(argv[5]) == "count";
     const size_t n = (size_t)(gib * (1ull << 30));
     uint8_t *d_src = nullptr, *d_hay = nullptr;
     uint64_t *d_res = nullptr;
@@ -48,20 +49,29 @@ int main(int argc, char **argv)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
+    auto once = [&]() -> int {
+        if (count_mode)
+            return ss_b200_count_in_device_async(s, d_hay, n, SS_B200_NPOS, d_ws, d_res, st);
+        return ss_b200_find_in_device_async(s, d_hay, n, 0, SS_B200_NPOS, d_ws, d_res, st);
+    };
     for (int rep = 0; rep < 3; rep++) {
         for (int i = 0; i < 3; i++)
-            CK(ss_b200_find_in_device_async(s, d_hay, n, 0, SS_B200_NPOS, d_ws, d_res, st));
+            CK(once());
         cudaEventRecord(e0, st);
         for (int i = 0; i < steps; i++)
-            CK(ss_b200_find_in_device_async(s, d_hay, n, 0, SS_B200_NPOS, d_ws, d_res, st));
+            CK(once());
         cudaEventRecord(e1, st);
         CK(cudaStreamSynchronize(st));
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         uint64_t r = 0;
         CK(cudaMemcpy(&r, d_res, 8, cudaMemcpyDeviceToHost));
-        printf("%s over %.3g GiB: %.4f ms/scan, %.1f GB/s, result %s\n", needle.c_str(), gib, ms / steps,
-               n / (ms / steps * 1e-3) / 1e9, r == SS_B200_DEVICE_NONE ? "none" : "found");
+        if (count_mode)
+            printf("count %s over %.3g GiB: %.4f ms/scan, %.1f GB/s, %llu occurrences\n", needle.c_str(), gib, ms / steps,
+                   n / (ms / steps * 1e-3) / 1e9, (unsigned long long)r);
+        else
+            printf("%s over %.3g GiB: %.4f ms/scan, %.1f GB/s, result %s\n", needle.c_str(), gib, ms / steps,
+                   n / (ms / steps * 1e-3) / 1e9, r == SS_B200_DEVICE_NONE ? "none" : "found");
     }
     return 0;
 }

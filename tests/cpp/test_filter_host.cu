@@ -59,7 +59,7 @@ static bool run_case(const Case &t, const std::vector<long long> &truth)
         std::vector<long long> here;
         uint32_t z[4] = {0, 0, 0, 0};
         const bool alive = exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, t.k,
-                                                    [&](uint32_t j) { return (uint32_t)t.needle[j]; }, z);
+                                                    [&](uint32_t j) { return 0x01010101u * (uint32_t)t.needle[j]; }, z);
         if (!alive && (z[0] | z[1] | z[2] | z[3])) {
             printf("exact_alive returned false with live positions\n");
             return false;
