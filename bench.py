@@ -247,7 +247,19 @@ def cpu_baseline(i386: bytes, needle: bytes, sample_gib: float):
         m, _bm = oracle.short_sweep(sw, want_bitmap=False)
         c3.append(time.perf_counter() - t0)
     assert int(offs.sum()) == 809985317 and m == 39105
+    import numpy as np
+
+    g_nd, g_hs, g_pn, g_ph, g_exp = random_grid()
+    g_pn_k, g_ph_k = np.tile(g_pn, 1000), np.tile(g_ph, 1000)
+    r_ = oracle.pairs(g_nd, g_hs, g_pn, g_ph)
+    assert [None if v == oracle.NPOS else int(v) for v in r_] == g_exp
+    gt = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        oracle.pairs(g_nd, g_hs, g_pn_k, g_ph_k)
+        gt.append(time.perf_counter() - t0)
     return {"value": round(one, 3), "unit": UNIT, "cores": 1, "kind": "port",
+            "random_bench_grid_ns_per_search": round(min(gt) * 1e9 / g_pn_k.size, 2),
             "config1_ipsum_i386_us": round(c1_us, 2), "config1_gbs_cache_resident": round(len(i386) / c1_us / 1e3, 2),
             "config2_literal_ms": round(min(c2) * 1e3, 3), "config3_short_ms": round(min(c3) * 1e3, 3),
             "sample": f"i386.txt tiled to {sample_gib:g} GiB in host DRAM, needle {needle!r} absent, "
@@ -352,7 +364,7 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
     out["rarest_position_gbs"] = rare
     # the histogram kernel itself: every byte of the 8 GiB haystack, and the 16 MiB sample used above
     hrow = {}
-    for label, sample in (("whole_haystack", 0), ("sample_16MiB", 16 << 20)):
+    for label, sample in (("every_byte_exact", hay.numel()), ("default_sample_16MiB", 0)):
         for _ in range(2):
             ss._check(ss.lib().ss_b200_byte_histogram_device_async(hay.data_ptr(), hay.numel(), sample,
                                                                    d_hist.data_ptr(),
@@ -492,7 +504,60 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         "ms_per_iteration": round(tbest * 1e3, 3), "ns_per_pair": round(tbest * 1e9 / 10513405, 4),
         "matches": int(matches), "readme_i7_6700_ms": 79.416,
     }
+    # SURVEY 8f-4, bench/benches/random.rs:12-99: prefixes of data/needle in prefixes of data/haystack, sizes
+    # {1,5,10,20,50,100,1000}, every needle size against every not-smaller haystack size (28 searches).
+    # Pure latency regime: one batched launch for the grid, and the grid replicated 1000x in one launch
+    # for a per-search figure; the CPU restatement's time is in cpu_baseline.random_bench_grid_ns_per_search.
+    import numpy as np
+
+    nd_blob, hs_blob, pn, ph, exp = random_grid()
+    gb = ss.Batch(nd_blob, hs_blob)
+    bm, offs = gb.search_pairs(pn, ph)
+    assert [None if v == ss.NPOS else int(v) for v in offs] == exp
+    t1 = None
+    for it in range(30):
+        t0 = time.perf_counter()
+        gb.search_pairs(pn, ph, want_offsets=False)
+        dt = time.perf_counter() - t0
+        if it:
+            t1 = dt if t1 is None else min(t1, dt)
+    pn_k, ph_k = np.tile(pn, 1000), np.tile(ph, 1000)
+    tk = None
+    for it in range(6):
+        t0 = time.perf_counter()
+        bmk, _ = gb.search_pairs(pn_k, ph_k, want_offsets=False)
+        dt = time.perf_counter() - t0
+        if it:
+            tk = dt if tk is None else min(tk, dt)
+    assert int(np.unpackbits(bmk.view(np.uint8)).sum()) == 1000 * sum(e is not None for e in exp)
+    out["random_bench_grid"] = {
+        "what": "bench/benches/random.rs:12-99: 28 (needle prefix, haystack prefix) searches, sizes 1..1000 bytes; "
+                "host arrays in and out, host wall clock",
+        "searches": len(pn), "found": sum(e is not None for e in exp),
+        "one_launch_for_the_grid_us": round(t1 * 1e6, 2),
+        "grid_x1000_in_one_launch_ns_per_search": round(tk * 1e9 / pn_k.size, 3),
+    }
     return out
+
+
+def random_grid():
+    """The (needle, haystack) prefixes of bench/benches/random.rs:12-99 and what each search must return."""
+    import numpy as np
+
+    with open(os.path.join(ROOT, "data", "haystack"), "rb") as f:
+        haystack = f.read()
+    with open(os.path.join(ROOT, "data", "needle"), "rb") as f:
+        needle = f.read()
+    sizes = [1, 5, 10, 20, 50, 100, 1000]
+    needles = [needle[:s_] for s_ in sizes]
+    hays = [haystack[:s_] for s_ in sizes]
+    pn = np.array([i for i in range(len(sizes)) for j in range(i, len(sizes))], np.uint32)
+    ph = np.array([j for i in range(len(sizes)) for j in range(i, len(sizes))], np.uint32)
+    exp = []
+    for a_, b_ in zip(pn, ph):
+        e = hays[b_].find(needles[a_])
+        exp.append(None if e < 0 else e)
+    return needles, hays, pn, ph, exp
 
 
 def periodic_matches(i386: bytes, needle: bytes):

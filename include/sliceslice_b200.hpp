@@ -46,7 +46,7 @@ inline void check(int rc)
     if (rc == SS_B200_E_POSITION || rc == SS_B200_E_EMPTY_NEEDLE)
         throw SearcherPanic(ss_b200_strerror(rc));
     std::string msg = ss_b200_strerror(rc);
-    if (rc == SS_B200_E_CUDA || rc == SS_B200_E_NOMEM)
+    if (rc == SS_B200_E_CUDA || rc == SS_B200_E_NOMEM || rc == SS_B200_E_NCCL || rc == SS_B200_E_ARG)
         msg += std::string(": ") + ss_b200_last_error();
     throw B200Error(msg);
 }
@@ -92,7 +92,8 @@ public:
     DeviceHaystack &operator=(const DeviceHaystack &) = delete;
     ~DeviceHaystack() { ss_b200_haystack_free(h_); }
     size_t len() const { return ss_b200_haystack_len(h_); }
-    // 256 byte counts (sample_bytes = 0: every byte), the input of with_rarest_position
+    // 256 byte counts (sample_bytes = 0: a 16 MiB sample, exact for shorter haystacks), the input of
+    // with_rarest_position
     std::vector<uint64_t> byte_histogram(size_t sample_bytes = 0) const
     {
         std::vector<uint64_t> hist(256);
@@ -209,5 +210,121 @@ private:
 using DynamicB200Searcher = detail::SearcherImpl<false>;
 // Drop-in for sliceslice::x86::Avx2Searcher (src/x86.rs:266-383): empty needle panics.
 using B200Searcher = detail::SearcherImpl<true>;
+
+// ---------------------------------------------------------------------------------------------
+// Every GPU of the box from one process (ss_b200_ctx).  The searcher surface stays the reference's;
+// the context adds WHERE the haystack lives: sharded over the devices, or a host slice striped over
+// all of them for the duration of one search_in.
+
+class Context;
+
+// One haystack as contiguous shards of start positions, shard d on device d of the context.
+class ShardedHaystack {
+public:
+    ShardedHaystack(ShardedHaystack &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
+    ShardedHaystack(const ShardedHaystack &) = delete;
+    ShardedHaystack &operator=(const ShardedHaystack &) = delete;
+    ~ShardedHaystack() { ss_b200_sharded_free(h_); }
+    size_t len() const { return ss_b200_sharded_len(h_); }
+    const ss_b200_sharded *raw() const { return h_; }
+
+private:
+    friend class Context;
+    explicit ShardedHaystack(ss_b200_sharded *h) : h_(h) {}
+    ss_b200_sharded *h_ = nullptr;
+};
+
+// A set of haystacks partitioned over the devices of a context (many-haystack mode).
+class ContextHaystackSet {
+public:
+    ContextHaystackSet(ContextHaystackSet &&o) noexcept : h_(std::exchange(o.h_, nullptr)) {}
+    ContextHaystackSet(const ContextHaystackSet &) = delete;
+    ContextHaystackSet &operator=(const ContextHaystackSet &) = delete;
+    ~ContextHaystackSet() { ss_b200_ctx_hayset_free(h_); }
+    size_t len() const { return ss_b200_ctx_hayset_len(h_); }
+    const ss_b200_ctx_hayset *raw() const { return h_; }
+
+private:
+    friend class Context;
+    explicit ContextHaystackSet(ss_b200_ctx_hayset *h) : h_(h) {}
+    ss_b200_ctx_hayset *h_ = nullptr;
+};
+
+class Context {
+public:
+    // ndev <= 0: every visible device
+    explicit Context(int ndev = 0, int exchange = SS_B200_EXCHANGE_HOST)
+    {
+        check(ss_b200_ctx_create(ndev, nullptr, &c_));
+        if (exchange != SS_B200_EXCHANGE_HOST)
+            set_exchange(exchange);
+    }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    ~Context() { ss_b200_ctx_free(c_); }
+    int device_count() const { return ss_b200_ctx_device_count(c_); }
+    void set_exchange(int kind) { check(ss_b200_ctx_set_exchange(c_, kind)); }
+
+    ShardedHaystack upload_sharded(Bytes host, size_t halo = 4096) const
+    {
+        ss_b200_sharded *h = nullptr;
+        check(ss_b200_sharded_upload(c_, host.ptr, host.len, halo, &h));
+        return ShardedHaystack(h);
+    }
+    ShardedHaystack sharded_from_device(const void *const *dptrs, const size_t *owned, const size_t *spans) const
+    {
+        ss_b200_sharded *h = nullptr;
+        check(ss_b200_sharded_from_device(c_, dptrs, owned, spans, &h));
+        return ShardedHaystack(h);
+    }
+    // searcher.search_in(haystack) with the haystack sharded over the devices (src/x86.rs:523)
+    template <bool STRICT>
+    bool search_in(const detail::SearcherImpl<STRICT> &s, const ShardedHaystack &h)
+    {
+        uint8_t found = 0;
+        check(ss_b200_search_sharded(c_, s.raw(), h.raw(), &found, nullptr));
+        return found != 0;
+    }
+    template <bool STRICT>
+    std::optional<size_t> find_in(const detail::SearcherImpl<STRICT> &s, const ShardedHaystack &h)
+    {
+        size_t off = SS_B200_NPOS;
+        check(ss_b200_find_sharded(c_, s.raw(), h.raw(), &off));
+        return off == SS_B200_NPOS ? std::nullopt : std::optional<size_t>(off);
+    }
+    // searcher.search_in(&[u8]) with ONE host slice striped over all devices / PCIe links
+    template <bool STRICT>
+    bool search_in(const detail::SearcherImpl<STRICT> &s, Bytes haystack)
+    {
+        uint8_t found = 0;
+        check(ss_b200_search_in_host_multi(c_, s.raw(), haystack.ptr, haystack.len, &found));
+        return found != 0;
+    }
+    template <bool STRICT>
+    std::optional<size_t> find_in(const detail::SearcherImpl<STRICT> &s, Bytes haystack)
+    {
+        size_t off = SS_B200_NPOS;
+        check(ss_b200_find_in_host_multi(c_, s.raw(), haystack.ptr, haystack.len, &off));
+        return off == SS_B200_NPOS ? std::nullopt : std::optional<size_t>(off);
+    }
+    // many-haystack mode: flags[h] = searcher.search_in(haystack h)
+    ContextHaystackSet upload_haystack_set(const uint8_t *blob, const uint64_t *offsets, size_t n) const
+    {
+        ss_b200_ctx_hayset *h = nullptr;
+        check(ss_b200_ctx_hayset_upload(c_, blob, offsets, n, &h));
+        return ContextHaystackSet(h);
+    }
+    template <bool STRICT>
+    std::vector<uint8_t> search_in(const detail::SearcherImpl<STRICT> &s, const ContextHaystackSet &set)
+    {
+        std::vector<uint8_t> flags(set.len());
+        check(ss_b200_ctx_hayset_search(c_, s.raw(), set.raw(), flags.data()));
+        return flags;
+    }
+    ss_b200_ctx *raw() const { return c_; }
+
+private:
+    ss_b200_ctx *c_ = nullptr;
+};
 
 } // namespace sliceslice_b200

@@ -122,7 +122,8 @@ struct ss_b200_ctx_hayset {
         ss_b200_hayset *set = nullptr;
         size_t blob_len = 0;
     };
-    const ss_b200_ctx *ctx = nullptr;
+    const ss_b200_ctx *ctx = nullptr; // identity only: the set may outlive its context (freeing uses `devices`)
+    std::vector<int> devices;
     size_t n = 0;
     std::vector<Part> parts;
 };
@@ -577,7 +578,7 @@ extern "C" void ss_b200_ctx_hayset_free(ss_b200_ctx_hayset *hs)
         return;
     for (size_t d = 0; d < hs->parts.size(); d++) {
         auto &p = hs->parts[d];
-        SsDeviceGuard g(hs->ctx->devices[d]);
+        SsDeviceGuard g(hs->devices[d]);
         ss_b200_hayset_free(p.set);
         cudaFree(p.blob);
         cudaFree(p.offsets);
@@ -606,6 +607,7 @@ extern "C" int ss_b200_ctx_hayset_upload(const ss_b200_ctx *c, const uint8_t *bl
         return SS_B200_E_NOMEM;
     const int nd = (int)c->devices.size();
     hs->ctx = c;
+    hs->devices = c->devices;
     hs->n = n;
     hs->parts.resize(nd);
     const uint64_t total = offsets[n];

@@ -4,6 +4,9 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace {
 std::atomic<uint64_t> g_launches{0};
@@ -61,6 +64,25 @@ static void choose_extra_anchors(ScanArgs &a, int allow)
     }
 }
 
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor per (kernel, dynamic smem), cached
+static int ss_tma_occupancy(const void *fn, size_t smem)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, size_t>, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(fn, smem);
+    auto it = cache.find(key);
+    if (it != cache.end())
+        return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, SS_TMA_THREADS, smem) != cudaSuccess) {
+        cudaGetLastError();
+        n = 2;
+    }
+    cache[key] = n;
+    return n;
+}
+
 cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, const SsDeviceInfo &dev,
                                 cudaStream_t stream)
 {
@@ -92,7 +114,8 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
         if (tile_kib != 16 && tile_kib != 32)
             tile_kib = (scan_bytes >= (2ull << 30)) ? 32 : 16;
         const uint32_t tile = (uint32_t)tile_kib * 1024u;
-        int stages = t.stages > 0 ? t.stages : (tile_kib == 32 ? 3 : 4);
+        // two CTAs per SM either way (register-bound): ~192 KB of loads in flight per SM
+        int stages = t.stages > 0 ? t.stages : (tile_kib == 32 ? 3 : 6);
         const uint32_t stage_stride = tile + ((halo + 127u) & ~127u);
         SsTmaFn fn = (tile_kib == 32) ? ss_table_tma_32(ws, bsz, qz, k1, xk) : ss_table_tma_16(ws, bsz, qz, k1, xk);
         size_t smem = (size_t)stages * stage_stride + (size_t)stages * 16 + (size_t)stages * 4 + 16;
@@ -105,7 +128,9 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
             return e;
         int per_sm = t.ctas_per_sm;
         if (per_sm <= 0) {
-            per_sm = (int)((size_t)dev.smem_per_sm / (smem + 1024));
+            // resident CTAs per SM as the hardware will grant them (shared memory AND registers): a grid
+            // larger than one wave would leave CTAs queued behind persistent ones
+            per_sm = ss_tma_occupancy((const void *)fn, smem);
             if (per_sm < 1)
                 per_sm = 1;
             if (per_sm > 4)

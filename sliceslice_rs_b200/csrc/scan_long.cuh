@@ -150,8 +150,8 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
         // has nothing left to decide
         // (only while this warp's previous hit path did flag something: an absent needle never pays
         // for the lookup)
-        if (many_hot && many_step_covered(a, (long long)(cw * 16ull) - (long long)a.head,
-                                          (long long)((cw + U * 32) * 16ull) - (long long)a.head - 1))
+        if (many_hot && many_step_done(a, (long long)(cw * 16ull) - (long long)a.head,
+                                       (long long)((cw + U * 32) * 16ull) - (long long)a.head - 1))
             return false;
         if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
@@ -165,7 +165,7 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
             if (fl[u] && (!CLAMP || c < a.n_chunks))
                 got += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
         }
-        if (a.seg_hint != nullptr)
+        if (a.seg_done != nullptr)
             many_hot = __any_sync(0xFFFFFFFFu, got != 0); // launch-uniform branch
         else
             occ += got;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
 // Dynamic smem layout: [stages][stage_stride] data, then full[stages], empty[stages] mbarriers,
 // then one uint32 "valid" word per stage (0 = producer stopped: early exit or end of work).
 template <int WS, bool BSZ, bool QZ, bool K1, int XK, int TILE>
-__global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
+__global__ void __launch_bounds__(SS_TMA_THREADS, 2)
     scan_tma_kernel(const __grid_constant__ ScanArgs a, int stages, uint32_t stage_stride, uint32_t halo)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
                     const unsigned long long sc0 = tile_c0 + (unsigned long long)(lc0 - lane);
                     // (only while this warp's previous hit path did flag something: an absent needle never
                     // pays for the lookup)
-                    if (many_hot && many_step_covered(a, (long long)(sc0 * 16ull) - (long long)a.head,
-                                                      (long long)((sc0 + 32 * U) * 16ull) - (long long)a.head - 1))
+                    if (many_hot && many_step_done(a, (long long)(sc0 * 16ull) - (long long)a.head,
+                                                   (long long)((sc0 + 32 * U) * 16ull) - (long long)a.head - 1))
                         continue;
                     if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, (TILE >= 32768 ? 2 : 3))
                         if (fl[u] && c < a.n_chunks)
                             got += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
                     }
-                    if (a.seg_hint != nullptr)
+                    if (a.seg_done != nullptr)
                         many_hot = __any_sync(0xFFFFFFFFu, got != 0); // launch-uniform branch
                     else
                         occ += got;

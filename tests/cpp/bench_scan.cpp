@@ -2,7 +2,7 @@
 // also the A/B harness for kernel changes: point LD_LIBRARY_PATH at another build of the library).
 //   g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include tests/cpp/bench_scan.cpp \
 //       -Lsliceslice_rs_b200 -lsliceslice_b200 -L/usr/local/cuda/lib64 -lcudart -o bench_scan
-//   bench_scan <i386.txt> [GiB = 8] [steps = 100] [needle = ipsum] [mode = find | count]
+//   bench_scan <i386.txt> [GiB = 8] [steps = 100] [needle = ipsum] [mode = find | count] [tile_kib = 0] [stages = 0]
 #include "sliceslice_b200.h"
 
 #include <cuda_runtime.h>
@@ -31,6 +31,8 @@ int main(int argc, char **argv)
     const int steps = argc > 3 ? atoi(argv[3]) : 100;
     const std::string needle = argc > 4 ? argv[4] : "ipsum";
     const bool count_mode = argc > 5 && std::string(argv[5]) == "count";
+    if (argc > 6)
+        CK(ss_b200_set_scan_tuning(0, 0, atoi(argv[6]), argc > 7 ? atoi(argv[7]) : 0));
     const size_t n = (size_t)(gib * (1ull << 30));
     uint8_t *d_src = nullptr, *d_hay = nullptr;
     uint64_t *d_res = nullptr;

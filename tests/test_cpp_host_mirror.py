@@ -84,6 +84,34 @@ def test_cpp_mirror_reference_test_shapes(binary):
     assert "ok:" in r.stdout
 
 
+@pytest.fixture(scope="module")
+def ctx_binary():
+    from sliceslice_rs_b200 import build
+
+    lib = build.build()
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "test_ctx")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+           os.path.join(ROOT, "tests", "cpp", "test_ctx.cpp"), "-o", exe, lib, "-L/usr/local/cuda/lib64", "-lcudart",
+           f"-Wl,-rpath,{os.path.dirname(lib)}", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_cpp_ctx_test_builds(ctx_binary):
+    assert os.path.exists(ctx_binary)
+
+
+@pytest.mark.gpu
+def test_cpp_multi_gpu_context(ctx_binary):
+    """tests/cpp/test_ctx.cpp: the multi-GPU context from a compiled host, on every GPU of the box --
+    sharded haystack through the three exchanges, one host slice striped over all devices, many-haystack
+    mode; expectations from a naive search."""
+    r = subprocess.run([ctx_binary, os.path.join(ROOT, "data", "i386.txt")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok:" in r.stdout
+
+
 def test_swar_identities_exhaustive():
     """All 2^32 words: the any-zero-byte test never misses or invents a candidate, and the exact mask
     marks exactly the zero bytes.  The formulas are checked to be the ones the kernels compile."""

@@ -575,6 +575,14 @@ def test_byte_histogram_and_rarest_position(i386, corpus):
     assert rc == 0
     assert np.array_equal(d_hist.cpu().numpy().astype(np.uint64), hist)
     hs.close()
+    # the default (sample_bytes == 0) is a 16 MiB sample: exact up to that size, the documented granule rule
+    # beyond it; sample_bytes >= len still counts every byte
+    long = (i386 * 25)[: (20 << 20) + 999]
+    hs = ss.DeviceHaystack.upload(long)
+    assert np.array_equal(hs.byte_histogram(), _sampled_hist(long, 16 << 20))
+    assert np.array_equal(hs.byte_histogram(len(long)),
+                          np.bincount(np.frombuffer(long, np.uint8), minlength=256).astype(np.uint64))
+    hs.close()
 
 
 def test_many_haystack_mode_vs_oracle(sorted_words, i386, variant):
