@@ -300,7 +300,7 @@ def reference_arm(args):
               f"a GB/s rate, so it compares with the full-size figure), needle {args.needle!r} absent, {cores} threads "
               f"over contiguous slices with a k-1 halo; C restatement of DynamicAvx2Searcher (gcc -O3 -mavx2)")
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -310,7 +310,7 @@ def reference_arm(args):
                          "single_thread": {"value": round(single, 3), "cores": 1,
                                            "sample": f"first {n1 / (1 << 30):g} GiB of the same buffer, best of 3"}},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 # ---------------------------------------------------------------------------------------------
@@ -740,7 +740,7 @@ def many_mode_run(args, ss, torch, dist, world, rank, local, steps, with_clocks=
 def many_mode(args, ss, torch, dist, world, rank, local):
     line = many_mode_run(args, ss, torch, dist, world, rank, local, args.steps)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def concurrent_h2d_gbs(torch, devices, nbytes=1 << 30, reps=3):
@@ -776,8 +776,31 @@ def concurrent_h2d_gbs(torch, devices, nbytes=1 << 30, reps=3):
     return [round(out[d], 2) for d in devices]
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print banners there (NCCL's version line comes
+    from C code, past sys.stdout): point fd 1 at stderr for the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    guard_stdout()
     strong = args.total_gib > 0
     if strong:
         args.gib = args.total_gib / max(int(os.environ.get("WORLD_SIZE", "1")), 1)
@@ -1232,7 +1255,7 @@ def main():
         }
         if extras:
             line["extras"] = extras
-        print(json.dumps(line), flush=True)
+        emit(line)
     if peer is not None:
         peer.close()
     if world > 1:

@@ -17,10 +17,30 @@ pub struct RawSearcher {
 pub struct RawHaystack {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct RawCtx {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct RawSharded {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct RawCtxHayset {
+    _p: [u8; 0],
+}
 
 pub const SS_B200_OK: c_int = 0;
 pub const SS_B200_E_POSITION: c_int = 1;
 pub const SS_B200_E_EMPTY_NEEDLE: c_int = 2;
+/// How `Context::search_in` MIN-reduces the per-shard first offsets (`enum ss_b200_exchange`).
+#[repr(i32)]
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum Exchange {
+    Host = 0,
+    Peer = 1,
+    Nccl = 2,
+}
 
 extern "C" {
     fn ss_b200_strerror(status: c_int) -> *const c_char;
@@ -39,6 +59,33 @@ extern "C" {
     fn ss_b200_find_in(s: *const RawSearcher, h: *const RawHaystack, offset: *mut usize) -> c_int;
     fn ss_b200_search_in_host(s: *const RawSearcher, host: *const u8, len: usize, found: *mut u8) -> c_int;
     fn ss_b200_find_in_host(s: *const RawSearcher, host: *const u8, len: usize, offset: *mut usize) -> c_int;
+    fn ss_b200_thread_release() -> c_int;
+    // multi-GPU context (one process, every GPU of the box)
+    fn ss_b200_ctx_create(ndev: c_int, devices: *const c_int, out: *mut *mut RawCtx) -> c_int;
+    fn ss_b200_ctx_free(ctx: *mut RawCtx);
+    fn ss_b200_ctx_device_count(ctx: *const RawCtx) -> c_int;
+    fn ss_b200_ctx_set_exchange(ctx: *mut RawCtx, kind: c_int) -> c_int;
+    fn ss_b200_sharded_upload(ctx: *const RawCtx, host: *const u8, len: usize, halo: usize, out: *mut *mut RawSharded) -> c_int;
+    fn ss_b200_sharded_from_device(ctx: *const RawCtx, dptrs: *const *const c_void, owned: *const usize,
+                                   spans: *const usize, out: *mut *mut RawSharded) -> c_int;
+    fn ss_b200_sharded_free(sh: *mut RawSharded);
+    fn ss_b200_sharded_len(sh: *const RawSharded) -> usize;
+    fn ss_b200_search_sharded(ctx: *mut RawCtx, s: *const RawSearcher, sh: *const RawSharded, found: *mut u8,
+                              global_offset: *mut usize) -> c_int;
+    fn ss_b200_find_in_host_multi(ctx: *mut RawCtx, s: *const RawSearcher, host: *const u8, len: usize,
+                                  offset: *mut usize) -> c_int;
+    fn ss_b200_search_in_host_multi(ctx: *mut RawCtx, s: *const RawSearcher, host: *const u8, len: usize,
+                                    found: *mut u8) -> c_int;
+    fn ss_b200_ctx_hayset_upload(ctx: *const RawCtx, blob: *const u8, offsets: *const u64, n: usize,
+                                 out: *mut *mut RawCtxHayset) -> c_int;
+    fn ss_b200_ctx_hayset_free(hs: *mut RawCtxHayset);
+    fn ss_b200_ctx_hayset_len(hs: *const RawCtxHayset) -> usize;
+    fn ss_b200_ctx_hayset_search(ctx: *mut RawCtx, s: *const RawSearcher, hs: *const RawCtxHayset, flags: *mut u8) -> c_int;
+}
+
+/// Frees the calling thread's streams, result slot and staging ring (they are also freed at thread exit).
+pub fn thread_release() {
+    check(unsafe { ss_b200_thread_release() });
 }
 
 fn check(rc: c_int) {
@@ -73,7 +120,8 @@ impl DeviceHaystack {
         check(ss_b200_haystack_from_device(dptr, len, &mut h));
         DeviceHaystack(h)
     }
-    /// 256 byte counts of the haystack (`sample_bytes == 0`: every byte), for `with_rarest_position`.
+    /// 256 byte counts of the haystack (`sample_bytes == 0`: a 16 MiB sample, exact for shorter haystacks;
+    /// `sample_bytes >= len`: every byte), for `with_rarest_position`.
     pub fn byte_histogram(&self, sample_bytes: usize) -> [u64; 256] {
         let mut hist = [0u64; 256];
         check(unsafe { ss_b200_haystack_byte_histogram(self.0, sample_bytes, hist.as_mut_ptr()) });
@@ -84,6 +132,11 @@ impl Drop for DeviceHaystack {
     fn drop(&mut self) {
         unsafe { ss_b200_haystack_free(self.0) }
     }
+}
+
+/// Implemented by both searcher flavours so that `Context` takes either.
+pub trait RawSearcherRef {
+    fn raw(&self) -> *const RawSearcher;
 }
 
 macro_rules! searcher {
@@ -146,6 +199,11 @@ macro_rules! searcher {
                 if off == usize::MAX { None } else { Some(off) }
             }
         }
+        impl<N: AsRef<[u8]>> RawSearcherRef for $name<N> {
+            fn raw(&self) -> *const RawSearcher {
+                self.raw
+            }
+        }
         impl<N: AsRef<[u8]>> Drop for $name<N> {
             fn drop(&mut self) {
                 unsafe { ss_b200_searcher_free(self.raw) }
@@ -158,3 +216,100 @@ searcher!(DynamicB200Searcher, ss_b200_searcher_new, ss_b200_searcher_with_posit
           "Drop-in for `sliceslice::x86::DynamicAvx2Searcher` (src/x86.rs:405-526).");
 searcher!(B200Searcher, ss_b200_searcher_new_strict, ss_b200_searcher_with_position_strict,
           "Drop-in for `sliceslice::x86::Avx2Searcher` (src/x86.rs:266-383): empty needle panics.");
+
+/// One haystack as contiguous shards of start positions, shard `d` on device `d` of a `Context`.
+pub struct ShardedHaystack(*mut RawSharded);
+impl ShardedHaystack {
+    pub fn len(&self) -> usize {
+        unsafe { ss_b200_sharded_len(self.0) }
+    }
+}
+impl Drop for ShardedHaystack {
+    fn drop(&mut self) {
+        unsafe { ss_b200_sharded_free(self.0) }
+    }
+}
+
+/// A set of haystacks partitioned over the devices of a `Context` (many-haystack mode).
+pub struct ContextHaystackSet(*mut RawCtxHayset);
+impl ContextHaystackSet {
+    pub fn len(&self) -> usize {
+        unsafe { ss_b200_ctx_hayset_len(self.0) }
+    }
+}
+impl Drop for ContextHaystackSet {
+    fn drop(&mut self) {
+        unsafe { ss_b200_ctx_hayset_free(self.0) }
+    }
+}
+
+/// Every GPU of the box from one process.  `&mut self` on the search calls: a context is used by one
+/// thread at a time (the searchers themselves stay `Send + Sync`).
+pub struct Context(*mut RawCtx);
+unsafe impl Send for Context {}
+impl Context {
+    /// `ndev == 0`: every visible device.
+    pub fn new(ndev: usize) -> Self {
+        let mut c = std::ptr::null_mut();
+        check(unsafe { ss_b200_ctx_create(ndev as c_int, std::ptr::null(), &mut c) });
+        Context(c)
+    }
+    pub fn device_count(&self) -> usize {
+        unsafe { ss_b200_ctx_device_count(self.0) as usize }
+    }
+    pub fn set_exchange(&mut self, kind: Exchange) {
+        check(unsafe { ss_b200_ctx_set_exchange(self.0, kind as c_int) });
+    }
+    /// Shards of `len / ndev` start positions each, every shard with `halo` more bytes: needles of up to
+    /// `halo + 1` bytes can be searched.
+    pub fn upload_sharded(&self, bytes: &[u8], halo: usize) -> ShardedHaystack {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ss_b200_sharded_upload(self.0, bytes.as_ptr(), bytes.len(), halo, &mut h) });
+        ShardedHaystack(h)
+    }
+    /// # Safety: `dptrs[d]` must point to `spans[d]` bytes on device `d` of the context, outliving the handle.
+    pub unsafe fn sharded_from_device(&self, dptrs: &[*const c_void], owned: &[usize], spans: &[usize]) -> ShardedHaystack {
+        assert!(dptrs.len() == self.device_count() && owned.len() == dptrs.len() && spans.len() == dptrs.len());
+        let mut h = std::ptr::null_mut();
+        check(ss_b200_sharded_from_device(self.0, dptrs.as_ptr(), owned.as_ptr(), spans.as_ptr(), &mut h));
+        ShardedHaystack(h)
+    }
+    /// `searcher.search_in(haystack)` with the haystack sharded over the devices.
+    pub fn search_in_sharded<S: RawSearcherRef>(&mut self, searcher: &S, haystack: &ShardedHaystack) -> bool {
+        self.find_in_sharded(searcher, haystack).is_some()
+    }
+    pub fn find_in_sharded<S: RawSearcherRef>(&mut self, searcher: &S, haystack: &ShardedHaystack) -> Option<usize> {
+        let (mut found, mut off) = (0u8, usize::MAX);
+        check(unsafe { ss_b200_search_sharded(self.0, searcher.raw(), haystack.0, &mut found, &mut off) });
+        if found != 0 { Some(off) } else { None }
+    }
+    /// `searcher.search_in(&[u8])` with ONE host slice striped over every device / PCIe link of the box.
+    pub fn search_in<S: RawSearcherRef>(&mut self, searcher: &S, haystack: &[u8]) -> bool {
+        let mut found = 0u8;
+        check(unsafe { ss_b200_search_in_host_multi(self.0, searcher.raw(), haystack.as_ptr(), haystack.len(), &mut found) });
+        found != 0
+    }
+    pub fn find_in<S: RawSearcherRef>(&mut self, searcher: &S, haystack: &[u8]) -> Option<usize> {
+        let mut off = usize::MAX;
+        check(unsafe { ss_b200_find_in_host_multi(self.0, searcher.raw(), haystack.as_ptr(), haystack.len(), &mut off) });
+        if off == usize::MAX { None } else { Some(off) }
+    }
+    /// Many-haystack mode: `blob` = concatenated haystacks, `offsets` = n + 1 ascending byte offsets.
+    pub fn upload_haystack_set(&self, blob: &[u8], offsets: &[u64]) -> ContextHaystackSet {
+        assert!(!offsets.is_empty() && offsets[0] == 0 && *offsets.last().unwrap() as usize == blob.len());
+        let mut h = std::ptr::null_mut();
+        check(unsafe { ss_b200_ctx_hayset_upload(self.0, blob.as_ptr(), offsets.as_ptr(), offsets.len() - 1, &mut h) });
+        ContextHaystackSet(h)
+    }
+    /// `flags[h] = searcher.search_in(haystack h)` for every haystack of the set.
+    pub fn search_in_set<S: RawSearcherRef>(&mut self, searcher: &S, set: &ContextHaystackSet) -> Vec<bool> {
+        let mut flags = vec![0u8; set.len()];
+        check(unsafe { ss_b200_ctx_hayset_search(self.0, searcher.raw(), set.0, flags.as_mut_ptr()) });
+        flags.into_iter().map(|f| f != 0).collect()
+    }
+}
+impl Drop for Context {
+    fn drop(&mut self) {
+        unsafe { ss_b200_ctx_free(self.0) }
+    }
+}

@@ -13,8 +13,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -522,7 +520,7 @@ __global__ void fill_flags_kernel(uint8_t *flags, unsigned long long n, uint8_t 
 
 int ss_capi_search_many(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets, size_t n_haystacks,
                         size_t blob_len, uint8_t *d_flags, void *workspace, const uint32_t *d_hint, size_t n_gran,
-                        uint8_t *d_done, void *stream)
+                        void *stream)
 {
     if (!s || !d_offsets || !d_flags || !workspace || (blob_len && !d_blob))
         return SS_B200_E_ARG;
@@ -555,10 +553,6 @@ int ss_capi_search_many(const ss_b200_searcher *s, const void *d_blob, const uin
     a.n_seg = n_haystacks;
     a.seg_hint = d_hint;
     a.n_gran = n_gran;
-    if (d_done) { // per-search scratch: one byte per SS_DONE_BLOCK bytes of blob, zero at the start
-        SS_CUDA(cudaMemsetAsync(d_done, 0, (blob_len >> SS_DONE_SHIFT) + 1, st));
-        a.seg_done = d_done;
-    }
     SS_CUDA(ss_host_launch_scan(a, ss_capi_tuning(), dev, st));
     return SS_B200_OK;
 }
@@ -567,8 +561,7 @@ extern "C" int ss_b200_search_many_async(const ss_b200_searcher *s, const void *
                                          size_t n_haystacks, size_t blob_len, uint8_t *d_flags, void *workspace,
                                          void *stream)
 {
-    return ss_capi_search_many(s, d_blob, d_offsets, n_haystacks, blob_len, d_flags, workspace, nullptr, 0, nullptr,
-                               stream);
+    return ss_capi_search_many(s, d_blob, d_offsets, n_haystacks, blob_len, d_flags, workspace, nullptr, 0, stream);
 }
 
 // Count mode: number of occurrences (overlapping ones included) of the needle in device memory.

@@ -150,4 +150,4 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searche
 // many-haystack scan shared by ss_b200_search_many_async (no hints) and ss_b200_hayset_search_async
 int ss_capi_search_many(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets, size_t n_haystacks,
                         size_t blob_len, uint8_t *d_flags, void *workspace, const uint32_t *d_hint, size_t n_gran,
-                        uint8_t *d_done, void *stream);
+                        void *stream);

@@ -9,8 +9,6 @@
 // needles are unaffected (7.0 TB/s either way).
 #include "capi_internal.h"
 
-#include <map>
-#include <mutex>
 #include <new>
 
 struct ss_b200_hayset {
@@ -20,10 +18,6 @@ struct ss_b200_hayset {
     size_t blob_len = 0;
     uint32_t *hint = nullptr; // n_gran entries, or nullptr when the set has 2^32 or more haystacks
     size_t n_gran = 0;
-    // per-search scratch ("done" blocks, ScanArgs::seg_done), one buffer per stream that has searched the
-    // set: searches of one set on different streams may run concurrently, those on one stream are ordered
-    mutable std::mutex mu;
-    mutable std::map<void *, uint8_t *> done_by_stream;
 };
 
 namespace {
@@ -98,8 +92,6 @@ extern "C" void ss_b200_hayset_free(ss_b200_hayset *hs)
         return;
     if (hs->hint)
         cudaFree(hs->hint);
-    for (auto &kv : hs->done_by_stream)
-        cudaFree(kv.second);
     delete hs;
 }
 
@@ -110,19 +102,8 @@ extern "C" int ss_b200_hayset_search_async(const ss_b200_searcher *s, const ss_b
 {
     if (!hs)
         return SS_B200_E_ARG;
-    uint8_t *done = nullptr;
-    if (hs->hint) {
-        std::lock_guard<std::mutex> lk(hs->mu);
-        auto it = hs->done_by_stream.find(stream);
-        if (it == hs->done_by_stream.end()) {
-            uint8_t *p = nullptr;
-            SS_CUDA(cudaMalloc(&p, (hs->blob_len >> SS_DONE_SHIFT) + 16));
-            it = hs->done_by_stream.emplace(stream, p).first;
-        }
-        done = it->second;
-    }
     return ss_capi_search_many(s, hs->blob, hs->offsets, hs->n, hs->blob_len, d_flags, workspace, hs->hint,
-                               hs->n_gran, done, stream);
+                               hs->n_gran, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -108,11 +108,12 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
         variant = 1; // second anchor too far away for a staged tile; LDG path handles any distance
 
     if (variant == 2) {
-        // measured (profiles/r01_size_sweep.txt): 16 KiB x 4 stages x 3 CTAs/SM wins up to ~1 GiB (more,
-        // smaller tiles spread a short scan better), 32 KiB x 3 stages x 2 CTAs/SM wins by 3-5 % beyond
+        // measured (profiles/r02_tile_choice.txt; both run two CTAs per SM, register-bound): 32 KiB x 3 stages
+        // wins or ties from 256 MiB up (6.1 vs 5.7-5.9 TB/s at 256 MiB, 6.7 vs 6.3 at 1 GiB), 16 KiB x 6 stages
+        // below (more, smaller tiles spread a short scan better: 4.1 vs 3.7 TB/s at 64 MiB)
         int tile_kib = t.tile_kib;
         if (tile_kib != 16 && tile_kib != 32)
-            tile_kib = (scan_bytes >= (2ull << 30)) ? 32 : 16;
+            tile_kib = (scan_bytes >= (128ull << 20)) ? 32 : 16;
         const uint32_t tile = (uint32_t)tile_kib * 1024u;
         // two CTAs per SM either way (register-bound): ~192 KB of loads in flight per SM
         int stages = t.stages > 0 ? t.stages : (tile_kib == 32 ? 3 : 6);

@@ -80,8 +80,7 @@ __device__ __forceinline__ FilterConsts load_filter_consts(const ScanArgs &a)
 // Returns true when the early-exit test says this CTA can stop.
 template <int WS, bool BSZ, bool QZ, bool K1, int XK, int U, bool CLAMP>
 __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restrict__ chunks, unsigned long long cw,
-                                         int lane, const FilterConsts &fc, AdaptiveFilter &af, uint32_t &occ,
-                                         bool &many_hot)
+                                         int lane, const FilterConsts &fc, AdaptiveFilter &af, uint32_t &occ)
 {
     // early exit: nothing at or right of this warp's first position can beat the current best
     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
@@ -146,29 +145,17 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
     if (XK != 0)
         af.end_tile(extras, slow ? 4u : 0u);
     if (slow) {
-        // many-haystack mode over a prepared set: a step that lies inside one already-flagged haystack
-        // has nothing left to decide
-        // (only while this warp's previous hit path did flag something: an absent needle never pays
-        // for the lookup)
-        if (many_hot && many_step_done(a, (long long)(cw * 16ull) - (long long)a.head,
-                                       (long long)((cw + U * 32) * 16ull) - (long long)a.head - 1))
-            return false;
         if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
             for (int u = 0; u < U; u++)
                 nx[u] = load_nx(u);
         }
-        uint32_t got = 0;
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const unsigned long long c = c0 + u * 32;
             if (fl[u] && (!CLAMP || c < a.n_chunks))
-                got += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
+                occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
         }
-        if (a.seg_done != nullptr)
-            many_hot = __any_sync(0xFFFFFFFFu, got != 0); // launch-uniform branch
-        else
-            occ += got;
     }
     return false;
 }
@@ -194,7 +181,6 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
     const FilterConsts fc = load_filter_consts(a);
     AdaptiveFilter af;
     uint32_t occ = 0; // count mode: occurrences seen by this thread
-    bool many_hot = false; // many-haystack mode: this warp's last hit path flagged a haystack
 
     // Programmatic dependent launch (scan_long.cu launches this variant with programmatic stream
     // serialisation): let the next kernel of the stream start launching now, and touch no global memory
@@ -210,17 +196,98 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
         bool stop;
         if (tile < n_interior) {
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af, occ, many_hot);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af, occ);
         } else {
             if (cw >= a.n_chunks)
                 continue; // this warp's run holds no start position (warp-uniform)
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af, occ, many_hot);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af, occ);
         }
         if (stop)
             break; // every later tile of this CTA is further right still
     }
     count_flush(a, occ);
     scan_finish(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// Many-haystack mode over a prepared set, one warp step (staged variant).  The per-match lookup of the
+// plain path (segment_hit: four to six DEPENDENT global loads per match) is what a needle that occurs in
+// most haystacks pays for.  Here the warp fetches, once per 4 KiB granule of blob (= its run of a tile),
+// the 32 haystack boundaries that follow the granule's first haystack into a shared-memory row -- one
+// hint load and one coalesced load of offsets -- and every lane then places its own matches with a
+// five-probe search of that row: no global load per match, one byte store per flagged haystack.
+// A match beyond the row (more than 32 boundaries inside 6 KiB: clusters of tiny haystacks) falls back
+// to segment_hit.  Flags are identical to the plain path.
+template <int WS, bool BSZ, bool K1, int U>
+__device__ __forceinline__ void many_step(const ScanArgs &a, const uint4 (&av)[U], const uint4 (&nx)[U],
+                                          const uint4 (&lo)[U], const uint4 (&hi)[U], const uint32_t (&fl)[U],
+                                          unsigned long long c_lane, int lane, unsigned long long *row,
+                                          unsigned long long &row_g, unsigned long long &row_h)
+{
+    FilterConsts fc;
+    fc.f4 = a.f4;
+    fc.l4 = a.l4;
+    fc.bs = a.bs;
+    uint32_t z[U][4];
+    bool mine = false;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        z[u][0] = z[u][1] = z[u][2] = z[u][3] = 0;
+        if (fl[u] && c_lane + u * 32 < a.n_chunks)
+            mine |= exact_alive<WS, BSZ, K1>(av[u], nx[u], lo[u], hi[u], fc, a.k,
+                                             [&](uint32_t j) { return a.needle4[j]; }, z[u]);
+    }
+    if (!__any_sync(0xFFFFFFFFu, mine))
+        return; // false candidates only: nothing to look up
+    long long p_first = (long long)((c_lane - lane) * 16ull) - (long long)a.head;
+    if (p_first < 0)
+        p_first = 0;
+    const unsigned long long g = (unsigned long long)p_first >> SS_HINT_SHIFT;
+    if (g != row_g) { // warp-uniform
+        const unsigned long long h_lo = __ldg(a.seg_hint + g); // last haystack starting at or before the granule
+        const unsigned long long idx = h_lo + 1 + lane;
+        const unsigned long long e = idx <= a.n_seg ? __ldg(a.seg_off + idx) : ~0ull;
+        __syncwarp(); // everybody is done with the previous row
+        row[lane] = e;
+        row_g = g;
+        row_h = h_lo;
+        __syncwarp();
+    }
+    if (!mine)
+        return;
+    const unsigned long long row_last = row[31];
+    unsigned long long flagged_until = 0; // positions below this lie in a haystack this lane has just flagged
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const long long p0 = (long long)((c_lane + u * 32) * 16ull) - (long long)a.head;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t zz = z[u][j];
+            while (zz) {
+                const int bit = __ffs((int)zz) - 1;
+                zz &= zz - 1;
+                const long long i = p0 + 4 * j + (bit >> 3);
+                if (i < 0 || (unsigned long long)i >= a.end || (unsigned long long)i < flagged_until)
+                    continue;
+                if (!K1 && a.k > 17u && !needle_rest_equal(a, a.hay + i, 17u))
+                    continue;
+                if (row_last <= (unsigned long long)i) { // beyond the row: the plain lookup
+                    flagged_until = segment_hit(a, (unsigned long long)i);
+                    continue;
+                }
+                uint32_t cnt = 0; // boundaries <= i among row[0..30] (row[31] > i)
+#pragma unroll
+                for (uint32_t sft = 16; sft; sft >>= 1)
+                    if (row[cnt + sft - 1] <= (unsigned long long)i)
+                        cnt += sft;
+                const unsigned long long e = row[cnt]; // end of the haystack holding i
+                if ((unsigned long long)i + a.k <= e) {
+                    a.seg_flags[row_h + cnt] = 1;
+                    flagged_until = e - a.k + 1;
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -301,7 +368,15 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, 2)
         const FilterConsts fc = load_filter_consts(a);
         AdaptiveFilter af;
         uint32_t occ = 0; // count mode: occurrences seen by this thread
-        bool many_hot = false; // many-haystack mode: this warp's last hit path flagged a haystack
+        // many-haystack mode over a prepared set: this warp's row of haystack boundaries (many_step)
+        __shared__ unsigned long long seg_rows[CW][32];
+        unsigned long long row_g = ~0ull, row_h = 0;
+        // count mode, needles of up to three bytes: with its anchors the filter word IS the whole compare
+        // (k == 1: first byte; k == 2: both bytes; k == 3: the middle byte is the extra anchor), so a zero
+        // byte of it is an occurrence.  While a warp sees occurrences in every step it counts them straight
+        // from the filter words -- branch-free, no hit path -- instead of flag + vote + verify.
+        const bool exact_kind = a.count != nullptr && (K1 || a.k == 2u || (XK == 3 && a.k == 3u));
+        bool count_hot = false;
         const uint32_t qb = a.q * 16u;
         int s = 0;
         uint32_t ph = 0;
@@ -313,6 +388,34 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, 2)
             const unsigned long long tile_c0 = tile * (unsigned long long)TILE_CHUNKS;
             constexpr int STEPS = WARP_CHUNKS / (32 * U);
             static_assert(STEPS == 1 || STEPS == 2 || STEPS == 4, "trip share is counted in quarters");
+            if (exact_kind && count_hot && tile_c0 * 16ull >= a.head &&
+                (tile_c0 + TILE_CHUNKS) * 16ull - a.head <= a.end) {
+                // every start position of the tile is in range: count from the filter words
+                uint32_t tocc = 0;
+#pragma unroll 1
+                for (int step = 0; step < STEPS; step++) {
+                    const uint32_t lc0 = (uint32_t)warp * WARP_CHUNKS + step * (32 * U) + lane;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const uint4 cav = lds16(st + (lc0 + u * 32) * 16u);
+                        const uint4 cnx = K1 ? cav : lds16(st + (lc0 + u * 32) * 16u + 16u);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            tocc += __popc(swar_zero_exact(filter_word<WS, BSZ, K1, XK>(cav, cnx, cav, cnx, j, fc)));
+                    }
+                }
+                occ += tocc;
+                // stay while the warp still finds a few occurrences per step; else back to the filter
+                count_hot = __reduce_add_sync(0xFFFFFFFFu, tocc) >= 4u * STEPS;
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&empty[s]);
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+                continue;
+            }
             const bool extras = (XK != 0) && af.begin_tile();
             uint32_t trips = 0;
 #pragma unroll 1
@@ -345,37 +448,30 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, 2)
                 }
                 const uint32_t any = step_flags<WS, BSZ, K1, XK, U>(av, nx, lo, hi, fc, extras, fl);
                 const bool slow = __any_sync(0xFFFFFFFFu, any != 0);
-                if (XK != 0)
-                    trips += slow ? 1u : 0u;
+                trips += slow ? 1u : 0u;
                 if (slow) {
-                    // many-haystack mode over a prepared set: a step that lies inside one already-flagged
-                    // haystack has nothing left to decide (warp-uniform)
-                    const unsigned long long sc0 = tile_c0 + (unsigned long long)(lc0 - lane);
-                    // (only while this warp's previous hit path did flag something: an absent needle never
-                    // pays for the lookup)
-                    if (many_hot && many_step_done(a, (long long)(sc0 * 16ull) - (long long)a.head,
-                                                   (long long)((sc0 + 32 * U) * 16ull) - (long long)a.head - 1))
-                        continue;
                     if (!NX_EAGER && !K1 && !extras) {
 #pragma unroll
                         for (int u = 0; u < U; u++)
                             nx[u] = lds16(st + (lc0 + u * 32) * 16u + 16u);
                     }
-                    uint32_t got = 0;
+                    if (a.seg_hint != nullptr) { // launch-uniform
+                        many_step<WS, BSZ, K1, U>(a, av, nx, lo, hi, fl, tile_c0 + lc0, lane, seg_rows[warp], row_g,
+                                                  row_h);
+                    } else {
 #pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const unsigned long long c = tile_c0 + lc0 + u * 32;
-                        if (fl[u] && c < a.n_chunks)
-                            got += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
+                        for (int u = 0; u < U; u++) {
+                            const unsigned long long c = tile_c0 + lc0 + u * 32;
+                            if (fl[u] && c < a.n_chunks)
+                                occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
+                        }
                     }
-                    if (a.seg_done != nullptr)
-                        many_hot = __any_sync(0xFFFFFFFFu, got != 0); // launch-uniform branch
-                    else
-                        occ += got;
                 }
             }
             if (XK != 0)
                 af.end_tile(extras, trips * (4u / STEPS));
+            if (exact_kind)
+                count_hot = trips == (uint32_t)STEPS; // every step of the tile saw an occurrence candidate
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&empty[s]);

@@ -21,8 +21,6 @@
 #define SS_MAILBOX_EMPTY 0xFFFFFFFFFFFFFFFFull     // never a result: offsets and NONE are <= INT64_MAX
 #define SS_HINT_SHIFT 12                           // segment lookup hints: one per 4 KiB of blob
 #define SS_HINT_GRANULE (1ull << SS_HINT_SHIFT)
-#define SS_DONE_SHIFT 11                           // "done" blocks of the many-haystack mode: 2 KiB, one warp step
-#define SS_DONE_BLOCK (1ull << SS_DONE_SHIFT)
 #define SS_NONE_U64 0x7FFFFFFFFFFFFFFFull // SS_B200_DEVICE_NONE
 #define SS_RESULT_PENDING 0xFFFFFFFFFFFFFFFFull // host-side marker of a mapped result slot before the kernel wrote it
 
@@ -77,10 +75,6 @@ struct ScanArgs {
     // holding blob byte g * SS_HINT_GRANULE, for g < n_gran; nullptr = plain binary search
     const uint32_t *seg_hint;
     unsigned long long n_gran;
-    // per-search scratch of a prepared set: one byte per SS_DONE_BLOCK bytes of blob, zero when the search
-    // starts; 1 = every start position of that block lies in a haystack that is already flagged, so a
-    // warp step inside such blocks has nothing left to decide (nullptr = no skipping)
-    uint8_t *seg_done;
     // count mode (nullptr otherwise): incremented once per occurrence
     unsigned long long *count;
     uint8_t needle_inline[SS_INLINE_NEEDLE_MAX]; // first min(k, 64) needle bytes
@@ -207,9 +201,7 @@ __device__ __forceinline__ uint8_t ld_relaxed_u8(const uint8_t *p)
 
 // Many-haystack mode: mark the haystack that wholly contains the match at blob position i.  Returns the
 // first start position behind which a match can no longer fall into that haystack (so the caller can
-// skip the other occurrences inside it), or 0 when nothing was flagged.  On a prepared set it also marks
-// the 2 KiB blocks whose every start position is now decided (their haystack is flagged), so that later
-// warp steps inside them skip their hit path with one byte load (many_step_done).
+// skip the other occurrences inside it), or 0 when nothing was flagged.
 static __device__ __noinline__ unsigned long long segment_hit(const ScanArgs &a, unsigned long long i)
 {
     // h = last segment with seg_off[h] <= i
@@ -232,40 +224,8 @@ static __device__ __noinline__ unsigned long long segment_hit(const ScanArgs &a,
     const unsigned long long e = __ldg(a.seg_off + lo + 1);
     if (i + a.k > e)
         return 0; // the match straddles the end of the haystack: it belongs to nobody
-    const unsigned long long until = e - a.k + 1; // start positions of this haystack end here
-    if (a.seg_done != nullptr && ld_relaxed_u8(a.seg_flags + lo) == 0) {
-        // first flagging seen by this lane: blocks [b0, b1) hold only start positions p with
-        // seg_off[lo] <= p and p + k <= e.  (Several lanes may do this at once: the stores are idempotent.)
-        const unsigned long long s0 = __ldg(a.seg_off + lo);
-        const unsigned long long b0 = (s0 + SS_DONE_BLOCK - 1) >> SS_DONE_SHIFT;
-        const unsigned long long b1 = until >> SS_DONE_SHIFT;
-        for (unsigned long long b = b0; b < b1; b++)
-            a.seg_done[b] = 1;
-    }
     a.seg_flags[lo] = 1;
-    return until;
-}
-
-// Many-haystack mode over a prepared set: are all start positions p_first .. p_last (one warp step) in
-// blocks marked done?  Then the step has nothing left to decide and its hit path is skipped.  A needle
-// present in most haystacks matches in almost every step; after the first match inside a haystack
-// everything else in it is redundant (one per haystack suffices: src/lib.rs:242-244 applied per
-// haystack).  Warp-uniform arguments (the loads broadcast); a block that is being marked right now may
-// still read 0, which only costs the work.
-__device__ __forceinline__ bool many_step_done(const ScanArgs &a, long long p_first, long long p_last)
-{
-    if (p_first < 0)
-        p_first = 0;
-    if (p_last >= (long long)a.end)
-        p_last = (long long)a.end - 1;
-    if (p_last < p_first)
-        return true; // no start position at all
-    const unsigned long long b0 = (unsigned long long)p_first >> SS_DONE_SHIFT;
-    const unsigned long long b1 = (unsigned long long)p_last >> SS_DONE_SHIFT;
-    bool done = ld_relaxed_u8(a.seg_done + b0) != 0;
-    if (b1 != b0)
-        done = done && ld_relaxed_u8(a.seg_done + b1) != 0 && b1 == b0 + 1;
-    return done;
+    return e - a.k + 1;
 }
 
 // What is left of the hit path once a chunk holds a position whose first min(k, 17) bytes equal the
@@ -303,7 +263,6 @@ static __device__ __noinline__ uint32_t hit_tail(const ScanArgs &a, uint32_t z0,
                 }
                 if (a.seg_off != nullptr) {
                     flagged_until = segment_hit(a, (unsigned long long)i);
-                    occ = 1; // "this step flagged something": switches the covered-step check on (scan_long.cuh)
                     continue;
                 }
                 // No fence: `key` is only ever touched with atomics and relaxed loads, and the acq_rel
@@ -330,8 +289,7 @@ static __device__ __noinline__ uint32_t hit_tail(const ScanArgs &a, uint32_t z0,
 // which cover needle bytes 0..16 of every start position of the chunk (exact_alive; inlined, needle
 // bytes as constant-bank operands).  The false candidates of natural text leave after one needle byte.
 // Count mode counts the survivors of an interior chunk with four popcounts; everything else that
-// survives goes through hit_tail.  Returns occurrences counted (count mode), 1 if a haystack was flagged
-// (many mode), else 0.
+// survives goes through hit_tail.  Returns occurrences counted (count mode), else 0.
 template <int WS, bool BSZ, bool K1>
 __device__ __forceinline__ uint32_t verify_chunk(const ScanArgs &a, const uint4 &av, const uint4 &nx, const uint4 &lo,
                                                  const uint4 &hi, unsigned long long chunk)

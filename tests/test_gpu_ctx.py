@@ -246,6 +246,51 @@ def test_ctx_hayset_vs_oracle(sorted_words, i386):
     ctx.close()
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+def test_many_mode_boundary_rows_and_count_from_filter_words(i386, variant):
+    """The staged variant's many-haystack step places matches with a shared-memory row of haystack
+    boundaries (fallback to the plain lookup beyond 32 boundaries), and its count mode counts needles of up
+    to three bytes straight from the filter words while they are frequent: unaligned blobs, runs of tiny
+    and empty haystacks, haystacks longer than a tile, needles longer than the register window."""
+    import random
+
+    ss.set_scan_variant(variant)
+    rng = random.Random(77)
+    lens = []
+    while sum(lens) < (9 << 20):
+        r = rng.random()
+        if r < 0.15:
+            lens += [rng.choice([0, 0, 1, 2, 3, 5, 9]) for _ in range(rng.randrange(1, 120))]  # clusters of tiny ones
+        elif r < 0.9:
+            lens.append(rng.randrange(0, 16384))
+        else:
+            lens.append(rng.randrange(30000, 90000))
+    text = i386 * (sum(lens) // len(i386) + 2)
+    for shift in (0, 5):
+        off = np.zeros(len(lens) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        blob = torch.frombuffer(bytearray(b"\0" * shift + text[:int(off[-1])]), dtype=torch.uint8).cuda()[shift:]
+        hays = [text[int(a):int(b)] for a, b in zip(off[:-1], off[1:])]
+        hs = ss.HaystackSet.from_device(blob, torch.from_numpy(off).cuda())
+        plain = ss.HaystackSet.from_device(blob, hs.offsets, prepared=False)
+        for nd in (b"the", b"e", b"segment", b"ipsum", b"descriptor table", b"the 80386 provides a", b"\n\n"):
+            s = ss.DynamicB200Searcher.new(nd)
+            got = s.search_many_async(hs).cpu().numpy().astype(bool)
+            assert got.tolist() == [nd in h for h in hays], (nd, shift)
+            assert np.array_equal(s.search_many_async(plain).cpu().numpy().astype(bool), got)
+        # count mode on the same (unaligned) bytes, with start limits that end inside a tile
+        ws = torch.zeros(32, dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        n = blob.numel()
+        for nd in (b"e", b" ", b"th", b"he", b"the", b"ing", b"zqj", b"\xff"):
+            s = ss.DynamicB200Searcher.new(nd)
+            for lim in (None, n // 2 + 12345, 70001):
+                s.count_in_async(blob, cnt, ws, start_limit=lim)
+                m = n if lim is None else lim + len(nd) - 1
+                assert int(cnt.item()) == oracle.count(text[:min(m, n)], nd), (nd, lim, shift)
+    ss.set_scan_variant(0)
+
+
 def test_peer_exchange_world1_mailbox_kernels():
     """ss_b200_find_in_device_exchange_async with world == 1: the scan's epilogue posts into the rank's
     own mailbox and mailbox_min_kernel collects it -- the whole fused-exchange code path on one GPU."""
