@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) triangular_kernel(const uint8_t *__restri
 // descriptors and the current per-needle best offsets are staged in shared memory once per CTA.  CTAs
 // are numbered segment-major so early segments run first and later ones are pruned by `best[w]` (the
 // reference's early return, src/lib.rs:242-244).  Candidates are verified from the register window as
-// in the long scan (verify_chunk), needle bytes coming from the L1-cached needle blob.
+// in the long scan (exact_alive), needle bytes coming from the L1-cached needle blob.
 #define SS_MN_THREADS 256
 #define SS_MN_U 2
 #define SS_MN_SEG_CHUNKS (SS_MN_THREADS * SS_MN_U)

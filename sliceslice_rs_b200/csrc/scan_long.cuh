@@ -6,7 +6,7 @@
 // tests the 16 start positions of one chunk per step with the SWAR two-anchor
 // filter (ss_device.cuh), a warp vote collapses the per-lane candidate flags,
 // and only warps that saw a candidate enter the exact decode + register-resident
-// verify (verify_chunk).  The leftmost match is kept with one atomicMax on
+// verify (step_alive_mask + hit_tail).  The leftmost match is kept with one atomicMax on
 // ~offset; tiles are visited in ascending order and a tile whose first position
 // lies beyond the current best is skipped (the reference's early return,
 // src/lib.rs:242-244, made parallel).  The same kernels also serve the count
@@ -150,12 +150,9 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
             for (int u = 0; u < U; u++)
                 nx[u] = load_nx(u);
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const unsigned long long c = c0 + u * 32;
-            if (fl[u] && (!CLAMP || c < a.n_chunks))
-                occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
-        }
+        // every start position of the step in range?  (warp-uniform; lets count mode popcount)
+        const bool interior = !CLAMP && cw * 16ull >= a.head && (cw + U * 32) * 16ull - a.head <= a.end;
+        occ += step_hits<WS, BSZ, K1, U>(a, av, nx, lo, hi, fl, c0, interior);
     }
     return false;
 }
@@ -217,27 +214,13 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
 // hint load and one coalesced load of offsets -- and every lane then places its own matches with a
 // five-probe search of that row: no global load per match, one byte store per flagged haystack.
 // A match beyond the row (more than 32 boundaries inside 6 KiB: clusters of tiny haystacks) falls back
-// to segment_hit.  Flags are identical to the plain path.
-template <int WS, bool BSZ, bool K1, int U>
-__device__ __forceinline__ void many_step(const ScanArgs &a, const uint4 (&av)[U], const uint4 (&nx)[U],
-                                          const uint4 (&lo)[U], const uint4 (&hi)[U], const uint32_t (&fl)[U],
-                                          unsigned long long c_lane, int lane, unsigned long long *row,
-                                          unsigned long long &row_g, unsigned long long &row_h)
+// to segment_hit.  Flags are identical to the plain path.  `m`: the lane's step_alive_mask.
+template <bool K1>
+__device__ __forceinline__ void many_step(const ScanArgs &a, unsigned long long m, unsigned long long c_lane, int lane,
+                                          unsigned long long *row, unsigned long long &row_g,
+                                          unsigned long long &row_h)
 {
-    FilterConsts fc;
-    fc.f4 = a.f4;
-    fc.l4 = a.l4;
-    fc.bs = a.bs;
-    uint32_t z[U][4];
-    bool mine = false;
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        z[u][0] = z[u][1] = z[u][2] = z[u][3] = 0;
-        if (fl[u] && c_lane + u * 32 < a.n_chunks)
-            mine |= exact_alive<WS, BSZ, K1>(av[u], nx[u], lo[u], hi[u], fc, a.k,
-                                             [&](uint32_t j) { return a.needle4[j]; }, z[u]);
-    }
-    if (!__any_sync(0xFFFFFFFFu, mine))
+    if (!__any_sync(0xFFFFFFFFu, m != 0))
         return; // false candidates only: nothing to look up
     long long p_first = (long long)((c_lane - lane) * 16ull) - (long long)a.head;
     if (p_first < 0)
@@ -253,39 +236,33 @@ __device__ __forceinline__ void many_step(const ScanArgs &a, const uint4 (&av)[U
         row_h = h_lo;
         __syncwarp();
     }
-    if (!mine)
+    if (m == 0)
         return;
     const unsigned long long row_last = row[31];
+    const long long p_lane = (long long)(c_lane * 16ull) - (long long)a.head; // position of byte 0 of chunk 0
     unsigned long long flagged_until = 0; // positions below this lie in a haystack this lane has just flagged
+#pragma unroll 1
+    while (m) {
+        const int bit = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const long long i = alive_bit_position(p_lane, bit);
+        if (i < 0 || (unsigned long long)i >= a.end || (unsigned long long)i < flagged_until)
+            continue;
+        if (!K1 && a.k > 17u && !needle_rest_equal(a, a.hay + i, 17u))
+            continue;
+        if (row_last <= (unsigned long long)i) { // beyond the row: the plain lookup
+            flagged_until = segment_hit(a, (unsigned long long)i);
+            continue;
+        }
+        uint32_t cnt = 0; // boundaries <= i among row[0..30] (row[31] > i)
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        const long long p0 = (long long)((c_lane + u * 32) * 16ull) - (long long)a.head;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t zz = z[u][j];
-            while (zz) {
-                const int bit = __ffs((int)zz) - 1;
-                zz &= zz - 1;
-                const long long i = p0 + 4 * j + (bit >> 3);
-                if (i < 0 || (unsigned long long)i >= a.end || (unsigned long long)i < flagged_until)
-                    continue;
-                if (!K1 && a.k > 17u && !needle_rest_equal(a, a.hay + i, 17u))
-                    continue;
-                if (row_last <= (unsigned long long)i) { // beyond the row: the plain lookup
-                    flagged_until = segment_hit(a, (unsigned long long)i);
-                    continue;
-                }
-                uint32_t cnt = 0; // boundaries <= i among row[0..30] (row[31] > i)
-#pragma unroll
-                for (uint32_t sft = 16; sft; sft >>= 1)
-                    if (row[cnt + sft - 1] <= (unsigned long long)i)
-                        cnt += sft;
-                const unsigned long long e = row[cnt]; // end of the haystack holding i
-                if ((unsigned long long)i + a.k <= e) {
-                    a.seg_flags[row_h + cnt] = 1;
-                    flagged_until = e - a.k + 1;
-                }
-            }
+        for (uint32_t sft = 16; sft; sft >>= 1)
+            if (row[cnt + sft - 1] <= (unsigned long long)i)
+                cnt += sft;
+        const unsigned long long e = row[cnt]; // end of the haystack holding i
+        if ((unsigned long long)i + a.k <= e) {
+            a.seg_flags[row_h + cnt] = 1;
+            flagged_until = e - a.k + 1;
         }
     }
 }
@@ -375,7 +352,7 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, 2)
         // (k == 1: first byte; k == 2: both bytes; k == 3: the middle byte is the extra anchor), so a zero
         // byte of it is an occurrence.  While a warp sees occurrences in every step it counts them straight
         // from the filter words -- branch-free, no hit path -- instead of flag + vote + verify.
-        const bool exact_kind = a.count != nullptr && (K1 || a.k == 2u || (XK == 3 && a.k == 3u));
+        const bool exact_kind = a.count != nullptr && a.filter_is_exact != 0u && (XK == 0 || XK == 3);
         bool count_hot = false;
         const uint32_t qb = a.q * 16u;
         int s = 0;
@@ -455,16 +432,15 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, 2)
                         for (int u = 0; u < U; u++)
                             nx[u] = lds16(st + (lc0 + u * 32) * 16u + 16u);
                     }
-                    if (a.seg_hint != nullptr) { // launch-uniform
-                        many_step<WS, BSZ, K1, U>(a, av, nx, lo, hi, fl, tile_c0 + lc0, lane, seg_rows[warp], row_g,
-                                                  row_h);
+                    const unsigned long long c_lane = tile_c0 + lc0;
+                    if (a.seg_hint != nullptr) { // launch-uniform: many-haystack mode over a prepared set
+                        const unsigned long long m = step_alive_mask<WS, BSZ, K1, U>(a, av, nx, lo, hi, fl, c_lane);
+                        many_step<K1>(a, m, c_lane, lane, seg_rows[warp], row_g, row_h);
                     } else {
-#pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            const unsigned long long c = tile_c0 + lc0 + u * 32;
-                            if (fl[u] && c < a.n_chunks)
-                                occ += verify_chunk<WS, BSZ, K1>(a, av[u], nx[u], lo[u], hi[u], c);
-                        }
+                        // every start position of the step in range?  (warp-uniform; lets count mode popcount)
+                        const unsigned long long sc0 = c_lane - lane;
+                        const bool interior = sc0 * 16ull >= a.head && (sc0 + 32 * U) * 16ull - a.head <= a.end;
+                        occ += step_hits<WS, BSZ, K1, U>(a, av, nx, lo, hi, fl, c_lane, interior);
                     }
                 }
             }

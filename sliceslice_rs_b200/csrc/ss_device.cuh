@@ -9,7 +9,7 @@
 // The SWAR test is exact as an "any candidate in this word" test (false positives
 // only above a true zero byte), so no candidate is ever missed; exact per-byte
 // decode and the memcmp verify (src/lib.rs:216-244) run on the hit path, out of the
-// same registers (verify_chunk).  Extra anchors may be folded into the filter where
+// same registers (step_alive_mask).  Extra anchors may be folded into the filter where
 // candidates are frequent (filter_word, AdaptiveFilter); they never change a result.
 #pragma once
 #include <cuda_runtime.h>
@@ -53,6 +53,9 @@ struct ScanArgs {
     uint32_t xk;   // extra-anchor kind the kernel was instantiated with (see filter_word)
     uint32_t e4[2]; // extra anchor bytes splatted x4
     uint32_t xbs;  // xk == 3: 8 * needle offset (1..3) of the unaligned extra anchor
+    // 1 when the anchors of the kernel's filter (first, `pos`, and the extra ones of kind xk) cover EVERY
+    // needle byte, i.e. a zero byte of the filter word is an occurrence (needles of up to three bytes)
+    uint32_t filter_is_exact;
     // peer exchange (n_peers == 0: off): the last CTA also stores the result into slot
     // [seq % 4][rank] of every rank's mailbox (peer memory over NVLink), fused into the scan epilogue
     unsigned long long *peer_slot[SS_MAX_PEERS];
@@ -228,88 +231,114 @@ static __device__ __noinline__ unsigned long long segment_hit(const ScanArgs &a,
     return e - a.k + 1;
 }
 
-// What is left of the hit path once a chunk holds a position whose first min(k, 17) bytes equal the
-// needle's (z: 0x80 in the byte of each such start position) -- rare unless the needle really occurs:
-// range check, the rest of a long needle from memory, and the action of the mode.
-//   first match  leftmost offset, early exit: CTA-level best first, the global word only when this lane
-//                lowered it, the stop words of the shards to the right on the GPU's first match
-//   count        every occurrence (overlapping ones included), no early exit; returns the number counted
-//                (the caller keeps the running total in a register, count_flush adds it once per warp)
-//   many         the blob is a concatenation of haystacks; flag the haystack that wholly contains the
-//                match, no early exit
-static __device__ __noinline__ uint32_t hit_tail(const ScanArgs &a, uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3,
-                                                 unsigned long long chunk)
+// The 0x80-per-alive-position words of one chunk (exact_alive) as 16 bits, bit p <-> start position p.
+__device__ __forceinline__ uint32_t pack_alive16(const uint32_t (&z)[4])
 {
-    const uint32_t z[4] = {z0, z1, z2, z3};
-    const long long p0 = (long long)(chunk * 16ull) - (long long)a.head; // position of byte 0 of the chunk
-    const bool one_byte = a.k == 1u;
-    uint32_t occ = 0;
-    unsigned long long flagged_until = 0; // many mode: positions below this lie in a haystack flagged just now
+    uint32_t b16 = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        uint32_t zz = z[j];
-        while (zz) {
-            const int bit = __ffs((int)zz) - 1;
-            zz &= zz - 1;
-            const long long i = p0 + 4 * j + (bit >> 3);
-            if (i < 0 || (unsigned long long)i >= a.end)
-                continue;
-            if (a.seg_off != nullptr && (unsigned long long)i < flagged_until)
-                continue;
-            if (one_byte || a.k <= 17u || needle_rest_equal(a, a.hay + i, 17u)) {
-                if (a.count != nullptr) {
-                    occ++;
-                    continue;
-                }
-                if (a.seg_off != nullptr) {
-                    flagged_until = segment_hit(a, (unsigned long long)i);
-                    continue;
-                }
-                // No fence: `key` is only ever touched with atomics and relaxed loads, and the acq_rel
-                // ticket of scan_finish (behind a CTA barrier) orders every atomicMax before the final read.
-                const unsigned long long old = atomicMin(&ss_cta_best, (unsigned long long)i);
-                if ((unsigned long long)i < old) {
-                    const unsigned long long prev = atomicMax(&a.ws->key, ~(unsigned long long)i);
-                    if (prev == 0ull) {
-                        // first match on this GPU: the shards to the right can stop (8-byte NVLink stores)
-                        for (uint32_t p = 0; p < a.n_stop_peers; p++)
-                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.stop_peer[p]), "l"(a.stop_seq)
-                                         : "memory");
-                    }
-                }
-                return 0; // ascending order: later positions of this chunk cannot be smaller
-            }
-        }
-    }
-    return occ;
+    for (int j = 0; j < 4; j++)
+        b16 |= ((((z[j] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * j); // bits 0, 8, 16, 24 -> bits 0..3
+    return b16;
 }
 
-// Hit path for one chunk whose SWAR flag fired -- the ctz loop + memcmp of src/lib.rs:216-248, done
-// without touching memory: the lane already holds the 32 haystack bytes [16c, 16c+32) in registers,
-// which cover needle bytes 0..16 of every start position of the chunk (exact_alive; inlined, needle
-// bytes as constant-bank operands).  The false candidates of natural text leave after one needle byte.
-// Count mode counts the survivors of an interior chunk with four popcounts; everything else that
-// survives goes through hit_tail.  Returns occurrences counted (count mode), else 0.
-template <int WS, bool BSZ, bool K1>
-__device__ __forceinline__ uint32_t verify_chunk(const ScanArgs &a, const uint4 &av, const uint4 &nx, const uint4 &lo,
-                                                 const uint4 &hi, unsigned long long chunk)
+// Hit path of one warp step, part 1 (inlined; no memory access): the exact compare of every flagged
+// chunk of the lane out of its registers -- the ctz loop + memcmp of src/lib.rs:216-248 for 16 start
+// positions at once (exact_alive; needle bytes as constant-bank operands).  The lane already holds the 32
+// haystack bytes [16c, 16c+32) of each of its U chunks, which cover needle bytes 0..16 of every start
+// position.  Returns one bit per start position whose first min(k, 17) bytes equal the needle's:
+// bit 16u + p <-> position p of the lane's chunk u (chunk u lies 32 chunks = 512 bytes behind chunk 0).
+// The false candidates of natural text leave after one needle byte and give 0.
+template <int WS, bool BSZ, bool K1, int U>
+__device__ __forceinline__ unsigned long long step_alive_mask(const ScanArgs &a, const uint4 (&av)[U],
+                                                              const uint4 (&nx)[U], const uint4 (&lo)[U],
+                                                              const uint4 (&hi)[U], const uint32_t (&fl)[U],
+                                                              unsigned long long c_lane)
 {
     FilterConsts fc;
     fc.f4 = a.f4;
     fc.l4 = a.l4;
     fc.bs = a.bs;
-    uint32_t z[4];
-    if (!exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, a.k, [&](uint32_t j) { return a.needle4[j]; }, z))
-        return 0;
-    if (a.count != nullptr && (K1 || a.k <= 17u)) {
-        const long long p0 = (long long)(chunk * 16ull) - (long long)a.head;
-        if (p0 >= 0 && (unsigned long long)p0 + 16ull <= a.end) {
-            // every surviving bit is an occurrence (the register window covered the whole needle) and
-            // every position of the chunk is in range: no bit loop
-            return __popc(z[0]) + __popc(z[1]) + __popc(z[2]) + __popc(z[3]);
+    unsigned long long m = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (fl[u] && c_lane + u * 32 < a.n_chunks) {
+            uint32_t z[4];
+            if (exact_alive<WS, BSZ, K1>(av[u], nx[u], lo[u], hi[u], fc, a.k, [&](uint32_t j) { return a.needle4[j]; }, z))
+                m |= (unsigned long long)pack_alive16(z) << (16 * u);
         }
     }
-    return hit_tail(a, z[0], z[1], z[2], z[3], chunk);
+    return m;
+}
+
+// Position of bit `bit` of a step_alive_mask whose chunk 0 starts at position p_lane.
+__device__ __forceinline__ long long alive_bit_position(long long p_lane, int bit)
+{
+    return p_lane + (long long)(bit >> 4) * 512 + (bit & 15);
+}
+
+// Hit path, part 2: what is left once a lane holds positions whose first min(k, 17) bytes equal the
+// needle's -- rare unless the needle really occurs.  One compact loop over the set bits: range check,
+// the rest of a long needle from memory, and the action of the mode.
+//   first match  leftmost offset, early exit: CTA-level best first, the global word only when this lane
+//                lowered it, the stop words of the shards to the right on the GPU's first match
+//   count        every occurrence (overlapping ones included), no early exit; returns the number counted
+//                (the caller keeps the running total in a register, count_flush adds it once per warp)
+//   many         the blob is a concatenation of haystacks; flag the haystack that wholly contains the
+//                match (plain lookup; the staged variant places matches of a prepared set itself), no early exit
+static __device__ __noinline__ uint32_t hit_tail(const ScanArgs &a, unsigned long long m, long long p_lane)
+{
+    const bool whole_needle_compared = a.k <= 17u;
+    uint32_t occ = 0;
+    unsigned long long flagged_until = 0; // many mode: positions below this lie in a haystack flagged just now
+#pragma unroll 1
+    while (m) {
+        const int bit = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const long long i = alive_bit_position(p_lane, bit);
+        if (i < 0 || (unsigned long long)i >= a.end)
+            continue;
+        if (a.seg_off != nullptr && (unsigned long long)i < flagged_until)
+            continue;
+        if (!whole_needle_compared && !needle_rest_equal(a, a.hay + i, 17u))
+            continue;
+        if (a.count != nullptr) {
+            occ++;
+            continue;
+        }
+        if (a.seg_off != nullptr) {
+            flagged_until = segment_hit(a, (unsigned long long)i);
+            continue;
+        }
+        // No fence: `key` is only ever touched with atomics and relaxed loads, and the acq_rel ticket of
+        // scan_finish (behind a CTA barrier) orders every atomicMax before the final read.
+        const unsigned long long old = atomicMin(&ss_cta_best, (unsigned long long)i);
+        if ((unsigned long long)i < old) {
+            const unsigned long long prev = atomicMax(&a.ws->key, ~(unsigned long long)i);
+            if (prev == 0ull) {
+                // first match on this GPU: the shards to the right can stop (8-byte NVLink stores)
+                for (uint32_t p = 0; p < a.n_stop_peers; p++)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.stop_peer[p]), "l"(a.stop_seq)
+                                 : "memory");
+            }
+        }
+        return 0; // ascending order: later positions of this lane cannot be smaller
+    }
+    return occ;
+}
+
+// Parts 1 + 2 for the modes that need no warp cooperation.  Count mode takes the survivors of an interior
+// step with one popcount (`interior`: every start position of the step is in range -- warp-uniform).
+template <int WS, bool BSZ, bool K1, int U>
+__device__ __forceinline__ uint32_t step_hits(const ScanArgs &a, const uint4 (&av)[U], const uint4 (&nx)[U],
+                                              const uint4 (&lo)[U], const uint4 (&hi)[U], const uint32_t (&fl)[U],
+                                              unsigned long long c_lane, bool interior)
+{
+    const unsigned long long m = step_alive_mask<WS, BSZ, K1, U>(a, av, nx, lo, hi, fl, c_lane);
+    if (m == 0)
+        return 0;
+    if (a.count != nullptr && a.k <= 17u && interior)
+        return (uint32_t)__popcll(m); // the register window covered the whole needle: every bit is an occurrence
+    return hit_tail(a, m, (long long)(c_lane * 16ull) - (long long)a.head);
 }
 
 // Count mode epilogue: add the warp's occurrences to *a.count with one atomic.  Called by whole,

@@ -16,6 +16,7 @@ run 8 20 th count
 run 8 20 segment count
 run 8 20 ipsum count
 run 8 20 zq count
+run 8 60 zq
 run 8 60 ipsum
 run 1 200 ipsum
 run 0.25 400 ipsum
