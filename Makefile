@@ -5,7 +5,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
 CSRC := sliceslice_rs_b200/csrc
 OBJDIR := sliceslice_rs_b200/_obj
-SRCS := capi.cu host_engine.cu capi_ctx.cu capi_exchange.cu scan_long.cu scan_ldg_u1.cu scan_ldg_u4.cu scan_tma_16.cu scan_tma_32.cu gen.cu batch.cu hist.cu hayset.cu
+SRCS := capi.cu host_engine.cu capi_ctx.cu capi_exchange.cu scan_long.cu scan_ldg_u1.cu scan_ldg_u4.cu scan_tma_16.cu scan_tma_32.cu gen.cu batch.cu hist.cu hayset.cu service.cu
 OBJS := $(addprefix $(OBJDIR)/,$(SRCS:.cu=.o))
 LIB := sliceslice_rs_b200/libsliceslice_b200.so
 

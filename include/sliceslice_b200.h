@@ -391,6 +391,14 @@ int ss_b200_set_extra_anchors(int n);
 /* The short-scan variant is launched with programmatic stream serialisation (back-to-back searches on
  * one stream overlap each launch with the previous scan): 1 = on (default), 0 = plain launches. */
 int ss_b200_set_launch_pdl(int on);
+/* Synchronous searches (ss_b200_find_in / ss_b200_search_in) over device-resident haystacks of up to
+ * 4 MiB with needles of up to 64 bytes do not launch a kernel per call: a resident grid per calling thread
+ * (at most four per device) polls a request word in mapped pinned memory and answers into another, so a
+ * call costs one PCIe round trip plus the scan -- the regime of the reference's per-needle loops
+ * (bench/benches/i386.rs:252-256).  The grid retires by itself idle_us after the last call (default 100;
+ * implicit synchronisations such as cudaFree wait at most that long) and at ss_b200_thread_release / thread
+ * exit.  on = 0: always launch (idle_us == 0 keeps the current value). */
+int ss_b200_set_sync_service(int on, int idle_us);
 /* Host-slice path (ss_b200_find_in_host / _multi):
  *   mode          0 auto (pinned slices up to 16 MiB in place, else the DMA ring), 1 always the DMA ring,
  *                 2 pinned input read in place by the direct-load kernel, 3 in place by the TMA kernel

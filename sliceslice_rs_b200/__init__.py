@@ -31,7 +31,7 @@ __all__ = ["DynamicB200Searcher", "B200Searcher", "DeviceHaystack", "SearcherPan
            "NPOS", "DEVICE_NONE", "fill_random", "fill_tiled", "set_scan_variant", "set_scan_tuning",
            "launch_count", "Batch", "set_extra_anchors", "HaystackSet", "rarest_position", "Context",
            "ShardedHaystack", "ContextHaystackSet", "set_host_path", "set_launch_pdl", "measure_h2d",
-           "thread_release", "thread_footprint", "E_NCCL", "EXCHANGE_HOST", "EXCHANGE_PEER", "EXCHANGE_NCCL"]
+           "thread_release", "thread_footprint", "set_sync_service", "E_NCCL", "EXCHANGE_HOST", "EXCHANGE_PEER", "EXCHANGE_NCCL"]
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 # SS_B200_LIB: load another build of the same ABI instead (A/B measurements of kernel changes)
@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         "ss_b200_set_extra_anchors": (i32, [i32]),
         "ss_b200_launch_count": (u64, []),
         "ss_b200_set_launch_pdl": (i32, [i32]),
+        "ss_b200_set_sync_service": (i32, [i32, i32]),
         "ss_b200_set_host_path": (i32, [i32, i32, i32]),
         "ss_b200_measure_h2d": (i32, [sz, i32, C.POINTER(C.c_double)]),
         "ss_b200_thread_release": (i32, []),
@@ -569,6 +570,12 @@ def launch_count() -> int:
 
 def set_launch_pdl(on: bool = True) -> None:
     _check(lib().ss_b200_set_launch_pdl(1 if on else 0))
+
+
+def set_sync_service(on: bool = True, idle_us: int = 0) -> None:
+    """Resident kernel for synchronous searches over short device-resident haystacks
+    (``ss_b200_set_sync_service``); ``idle_us`` = 0 keeps the current idle time."""
+    _check(lib().ss_b200_set_sync_service(1 if on else 0, idle_us))
 
 
 def set_host_path(mode: int = 0, chunk_mib: int = 0, copy_threads: int = -1) -> None:

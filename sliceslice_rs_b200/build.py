@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_obj")
 LIB = os.path.join(PKG, "libsliceslice_b200.so")
 SOURCES = ["capi.cu", "host_engine.cu", "capi_ctx.cu", "capi_exchange.cu", "scan_long.cu", "scan_ldg_u1.cu", "scan_ldg_u4.cu", "scan_tma_16.cu", "scan_tma_32.cu", "gen.cu",
-           "batch.cu", "hist.cu", "hayset.cu"]
+           "batch.cu", "hist.cu", "hayset.cu", "service.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -58,6 +58,7 @@ namespace {
 struct AtomicTuning {
     std::atomic<int> variant{0}, ctas_per_sm{0}, unroll{0}, tile_kib{0}, stages{0}, extra_anchors{-1}, pdl{1};
     std::atomic<int> host_mode{0}, host_chunk_mib{0}, host_copy_threads{-1};
+    std::atomic<int> service_on{1}, service_idle_us{100};
 } g_tuning;
 std::mutex g_dev_mutex;
 std::map<int, SsDeviceInfo> g_devs;
@@ -143,6 +144,20 @@ extern "C" int ss_b200_set_host_path(int mode, int chunk_mib, int copy_threads)
     g_tuning.host_mode = mode;
     g_tuning.host_chunk_mib = chunk_mib;
     g_tuning.host_copy_threads = copy_threads;
+    return SS_B200_OK;
+}
+void ss_capi_service_tuning(int *on, unsigned *idle_us)
+{
+    *on = g_tuning.service_on.load(std::memory_order_relaxed);
+    *idle_us = (unsigned)g_tuning.service_idle_us.load(std::memory_order_relaxed);
+}
+extern "C" int ss_b200_set_sync_service(int on, int idle_us)
+{
+    if ((on != 0 && on != 1) || idle_us < 0 || idle_us > 1000000)
+        return SS_B200_E_ARG;
+    g_tuning.service_on = on;
+    if (idle_us > 0)
+        g_tuning.service_idle_us = idle_us;
     return SS_B200_OK;
 }
 extern "C" uint64_t ss_b200_launch_count(void) { return ss_host_launch_count(); }
@@ -243,6 +258,7 @@ extern "C" int ss_b200_haystack_upload(const uint8_t *host, size_t len, ss_b200_
     h->dptr = d;
     h->len = len;
     h->owned = true;
+    h->plain_device_memory = true;
     h->device = dev;
     *out = h;
     return SS_B200_OK;
@@ -257,6 +273,15 @@ extern "C" int ss_b200_haystack_from_device(const void *dptr, size_t len, ss_b20
     h->dptr = (const uint8_t *)dptr;
     h->len = len;
     h->owned = false;
+    if (dptr) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dptr) == cudaSuccess) {
+            h->plain_device_memory = at.type == cudaMemoryTypeDevice;
+            h->device = at.device;
+        } else {
+            cudaGetLastError();
+        }
+    }
     *out = h;
     return SS_B200_OK;
 }
@@ -296,6 +321,10 @@ void SsLane::release()
         return;
     // at process teardown the runtime may already be gone: every call below then fails harmlessly
     SsDeviceGuard guard(device);
+    if (service) {
+        ss_service_release(service); // retires the resident kernel first
+        service = nullptr;
+    }
     if (stream)
         cudaStreamSynchronize(stream);
     if (copy_stream)
@@ -594,9 +623,21 @@ extern "C" int ss_b200_count_in_device_async(const ss_b200_searcher *s, const vo
 
 // One synchronous scan of device-visible memory on a given lane (its device is made current for the call).
 int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                         int force_variant)
+                         int force_variant, bool plain_device_memory)
 {
     SsDeviceGuard guard(c->device);
+    if (plain_device_memory && force_variant == 0 && ss_service_eligible(s, len)) {
+        // short device-resident haystack: through the resident kernel, no launch (service.cu)
+        int on = 0;
+        unsigned idle_us = 0;
+        ss_capi_service_tuning(&on, &idle_us);
+        if (on) {
+            bool used = false;
+            int rc = ss_service_find(c, s, dptr, len, idle_us, offset, &used);
+            if (rc != SS_B200_OK || used)
+                return rc;
+        }
+    }
     SsDeviceInfo dev;
     int rc = device_info(dev);
     if (rc != SS_B200_OK)
@@ -622,7 +663,7 @@ int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr,
 
 // One synchronous scan of device memory through the calling thread's lane.
 int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                             int force_variant)
+                             int force_variant, bool plain_device_memory)
 {
     const size_t k = s->needle.size();
     if (k == 0) { // DynamicAvx2Searcher::N0 => true, even for an empty haystack (src/x86.rs:470,500)
@@ -639,14 +680,14 @@ int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t
     int rc = ss_capi_get_lane(&c);
     if (rc != SS_B200_OK)
         return rc;
-    return ss_capi_find_on_lane(c, s, dptr, len, offset, force_variant);
+    return ss_capi_find_on_lane(c, s, dptr, len, offset, force_variant, plain_device_memory);
 }
 
 extern "C" int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t *offset)
 {
     if (!s || !h || !offset)
         return SS_B200_E_ARG;
-    return ss_capi_find_device_sync(s, h->dptr, h->len, offset, 0);
+    return ss_capi_find_device_sync(s, h->dptr, h->len, offset, 0, h->plain_device_memory);
 }
 
 extern "C" int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haystack *h, uint8_t *found)
@@ -654,7 +695,7 @@ extern "C" int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haysta
     if (!s || !h || !found)
         return SS_B200_E_ARG;
     size_t off = SS_B200_NPOS;
-    int rc = ss_capi_find_device_sync(s, h->dptr, h->len, &off, 0);
+    int rc = ss_capi_find_device_sync(s, h->dptr, h->len, &off, 0, h->plain_device_memory);
     if (rc == SS_B200_OK)
         *found = (off != SS_B200_NPOS) ? 1 : 0;
     return rc;

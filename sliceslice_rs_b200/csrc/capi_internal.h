@@ -45,6 +45,7 @@ struct ss_b200_haystack {
     const uint8_t *dptr = nullptr;
     size_t len = 0;
     bool owned = false;
+    bool plain_device_memory = false; // cudaMalloc-style memory (not managed, not mapped host): checked once
     int device = -1;
 };
 
@@ -78,6 +79,7 @@ struct SsLane {
     unsigned long long *chunk_results = nullptr; // pinned + mapped, one per chunk of a host-slice search
     unsigned long long *chunk_results_dev = nullptr;
     size_t chunk_results_cap = 0;
+    void *service = nullptr; // resident scan kernel of the synchronous short-haystack calls (service.cu)
 
     SsLane() = default;
     SsLane(const SsLane &) = delete;
@@ -109,9 +111,15 @@ struct SsDeviceGuard {
 // one synchronous scan of device-visible memory through the calling thread's lane
 // (force_variant: 0 = the process-wide tuning, 1 / 2 = that scan variant for this call)
 int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                             int force_variant);
+                             int force_variant, bool plain_device_memory = false);
 int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                         int force_variant);
+                         int force_variant, bool plain_device_memory = false);
+// service.cu: the resident kernel of the synchronous short-haystack calls
+bool ss_service_eligible(const ss_b200_searcher *s, size_t len);
+int ss_service_find(SsLane *lane, const ss_b200_searcher *s, const void *dptr, size_t len, unsigned idle_us,
+                    size_t *offset, bool *used);
+void ss_service_release(void *service);
+void ss_capi_service_tuning(int *on, unsigned *idle_us);
 // spin on a mapped result word until the kernel behind it has written it (or its stream reports an error)
 int ss_capi_wait_slot(volatile unsigned long long *word, unsigned long long pending, cudaStream_t stream);
 // host slices up to this size are searched in place from a mapped pinned copy (host_engine.cu)

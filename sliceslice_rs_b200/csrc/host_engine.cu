@@ -2,8 +2,9 @@
 //
 // One engine serves ss_b200_find_in_host (one device: the calling thread's lane) and
 // ss_b200_find_in_host_multi (capi_ctx.cu: one lane per device of a context).  The slice is cut into
-// chunks of start positions; chunk i goes to lane i % n_lanes, so the devices sweep the slice as one
-// band and all PCIe links are busy from the first chunk on.  Per lane the chunks run through a ring of
+// chunks of start positions, handed out in ascending order to whichever lane has room, so the devices
+// sweep the slice as one band, all PCIe links are busy from the first chunk on, and a faster link simply
+// takes more chunks.  Per lane the chunks run through a ring of
 // three device buffers: the H2D copy of chunk j+1 (copy stream) overlaps the scan of chunk j (scan
 // stream), each scan writes its result into a mapped pinned word.  The host never runs more than the
 // ring depth ahead of the results it has seen, so a match stops the feeding within a few chunks -- the
@@ -291,11 +292,11 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searche
             if (rc != SS_B200_OK)
                 return rc;
         }
-        const size_t mine = (n_chunks - l + used_lanes - 1) / used_lanes;
-        rc = ensure_chunk_results(c, mine);
+        // chunks go to whichever lane has room (below), so any lane may end up with any number of them
+        rc = ensure_chunk_results(c, n_chunks);
         if (rc != SS_B200_OK)
             return rc;
-        for (size_t j = 0; j < mine; j++)
+        for (size_t j = 0; j < n_chunks; j++)
             c->chunk_results[j] = SS_RESULT_PENDING;
         // needle fields once per lane; the geometry is redone per chunk
         rc = ss_capi_build_args(s, inplace ? (const void *)dev_view : (const void *)c->dbuf[0], k, 0, (size_t)-1,
@@ -334,23 +335,47 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searche
         }
         return false;
     };
+    int rr = 0; // where the search for a free lane starts: round robin among equally loaded lanes
     for (size_t i = 0; i < n_chunks && rc == SS_B200_OK && !hit; i++) {
-        const int l = (int)(i % used_lanes);
-        const size_t j = i / used_lanes; // index of the chunk within its lane
-        SsLane *c = lanes[l];
-        const int b = (int)(j % SsLane::NBUF);
-        // any finished chunk (of any lane) with a match ends the feeding: the reference would have
-        // returned already (src/lib.rs:242-244)
-        for (int l2 = 0; l2 < used_lanes && !hit; l2++)
-            hit = consume(l2);
-        // bounded run-ahead: at most NBUF chunks of a lane are in flight (its ring has NBUF buffers)
-        while (!hit && rc == SS_B200_OK && issued[l] - seen[l] >= (size_t)SsLane::NBUF) {
-            rc = ss_capi_wait_slot(c->chunk_results + seen[l], SS_RESULT_PENDING, c->stream);
-            if (rc == SS_B200_OK)
-                hit = consume(l);
+        // Which lane takes chunk i?  The one with the fewest chunks in flight -- NOT i % lanes: the PCIe
+        // links of a box are not equally fast when all are busy (measured on 8 x B200: four GPUs behind one
+        // shared upstream get 23 GB/s each, the other four 35 GB/s; profiles/r02_host_path_n8.json), and a
+        // static deal runs every link at the pace of the slowest.  A lane holds at most NBUF chunks (its ring
+        // has NBUF buffers): with every lane full, wait for whichever result arrives first.
+        int l = -1;
+        unsigned spins = 0;
+        while (!hit && rc == SS_B200_OK) {
+            // any finished chunk (of any lane) with a match ends the feeding: the reference would have
+            // returned already (src/lib.rs:242-244)
+            for (int l2 = 0; l2 < used_lanes && !hit; l2++)
+                hit = consume(l2);
+            if (hit)
+                break;
+            size_t best_load = (size_t)SsLane::NBUF;
+            for (int t = 0; t < used_lanes; t++) {
+                const int cand = (rr + t) % used_lanes;
+                const size_t load = issued[cand] - seen[cand];
+                if (load < best_load) {
+                    best_load = load;
+                    l = cand;
+                }
+            }
+            if (l >= 0)
+                break;
+            if ((++spins & 0x3FFF) == 0) { // every lane is full: keep an eye on the streams while spinning
+                for (int l2 = 0; l2 < used_lanes; l2++) {
+                    cudaError_t eq = cudaStreamQuery(lanes[l2]->stream);
+                    if (eq != cudaSuccess && eq != cudaErrorNotReady)
+                        rc = ss_capi_cuda_fail(eq, "host-slice scan");
+                }
+            }
         }
         if (hit || rc != SS_B200_OK)
             break;
+        rr = (l + 1) % used_lanes;
+        const size_t j = issued[l]; // index of the chunk within its lane
+        SsLane *c = lanes[l];
+        const int b = (int)(j % SsLane::NBUF);
         cudaError_t e = make_current(c->device);
         if (e != cudaSuccess) {
             rc = ss_capi_cuda_fail(e, "cudaSetDevice");
@@ -414,8 +439,7 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searche
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess && rc == SS_B200_OK)
             rc = ss_capi_cuda_fail(e, "cudaStreamSynchronize(host-slice)");
-        const size_t mine = submitted > (size_t)l ? (submitted - l + used_lanes - 1) / used_lanes : 0;
-        for (size_t j = 0; j < mine; j++) {
+        for (size_t j = 0; j < issued[l]; j++) {
             const unsigned long long v = c->chunk_results[j];
             if (v == SS_RESULT_PENDING) {
                 if (rc == SS_B200_OK) {

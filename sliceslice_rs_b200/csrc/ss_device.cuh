@@ -151,6 +151,21 @@ struct AdaptiveFilter {
     }
 };
 
+// haystack loads of the slow tail: through L2 only (ld.global.cg), because the resident service kernel
+// (service.cu) outlives host-side writes to the haystack and must never see a stale L1 line
+__device__ __forceinline__ uint32_t ld_hay_u8(const uint8_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_hay_u64(const uint8_t *p)
+{
+    unsigned long long v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
 // memcmp of needle[from..k) against h[from..k) from global memory -- only reached by needles longer
 // than the 17 bytes the register window covers, after those 17 bytes already matched.
 static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const uint8_t *h, uint32_t from)
@@ -158,7 +173,7 @@ static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const u
     const uint32_t k = a.k;
     if (k <= SS_INLINE_NEEDLE_MAX) {
         for (uint32_t j = from; j < k; j++)
-            if (__ldg(h + j) != a.needle_inline[j])
+            if (ld_hay_u8(h + j) != a.needle_inline[j])
                 return false;
         return true;
     }
@@ -166,10 +181,10 @@ static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const u
     uint32_t j = from;
     // byte steps until h + j is 8-byte aligned, then 8 bytes of haystack per step
     for (; j < k && ((reinterpret_cast<uintptr_t>(h + j)) & 7); j++)
-        if (__ldg(h + j) != __ldg(nd + j))
+        if (ld_hay_u8(h + j) != __ldg(nd + j))
             return false;
     for (; j + 8 <= k; j += 8) {
-        unsigned long long hv = __ldg(reinterpret_cast<const unsigned long long *>(h + j));
+        unsigned long long hv = ld_hay_u64(h + j);
         unsigned long long nv = 0;
 #pragma unroll
         for (int t = 0; t < 8; t++)
@@ -178,7 +193,7 @@ static __device__ __noinline__ bool needle_rest_equal(const ScanArgs &a, const u
             return false;
     }
     for (; j < k; j++)
-        if (__ldg(h + j) != __ldg(nd + j))
+        if (ld_hay_u8(h + j) != __ldg(nd + j))
             return false;
     return true;
 }

@@ -1,13 +1,14 @@
 // bench_latency.cpp -- per-call latency of the C-ABI entry points (development tool).
 //   g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include tests/cpp/bench_latency.cpp \
 //       -Lsliceslice_rs_b200 -lsliceslice_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/sliceslice_rs_b200
-//   bench_latency <i386.txt> <words.txt>
+//   bench_latency <i386.txt> <words.txt> [service = 1 | 0]   (0: one kernel launch per synchronous call)
 #include "sliceslice_b200.hpp"
 
 #include <cuda_runtime.h>
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iterator>
 #include <string>
@@ -40,6 +41,9 @@ int main(int argc, char **argv)
             a = b + 1;
         }
     }
+    if (argc > 3)
+        check(ss_b200_set_sync_service(atoi(argv[3]), 0));
+    printf("resident service kernel for synchronous calls: %s\n", (argc > 3 && atoi(argv[3]) == 0) ? "off" : "on");
     DeviceHaystack hay = DeviceHaystack::upload(i386);
     std::vector<DynamicB200Searcher> searchers;
     for (auto &w : words)

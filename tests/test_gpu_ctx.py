@@ -291,6 +291,75 @@ def test_many_mode_boundary_rows_and_count_from_filter_words(i386, variant):
     ss.set_scan_variant(0)
 
 
+def test_resident_service_kernel_for_synchronous_calls(i386, words):
+    """Synchronous find_in over a short device-resident haystack goes through the resident kernel (no
+    launch per call): same answers as the launched kernels, across idle retirements, haystack rewrites
+    between calls, alignments, needle lengths up to 64 and beyond (which fall back to a launch), more
+    threads than service slots, and thread_release with a grid resident."""
+    import threading
+    import time
+
+    hs = ss.DeviceHaystack.upload(i386)
+    sample = words[::23] + [b"ipsum", b"x", b"\n\n", i386[1000:1064], i386[5000:5065], i386[857000:857300]]
+    ss.set_sync_service(False)
+    launched = [ss.DynamicB200Searcher.new(w).find_in(hs) for w in sample]
+    assert launched == [(lambda e: None if e < 0 else e)(i386.find(w)) for w in sample]
+    ss.set_sync_service(True, 100)
+    l0 = ss.launch_count()
+    searchers = [ss.DynamicB200Searcher.new(w) for w in sample]
+    for rep in range(3):
+        assert [s.find_in(hs) for s in searchers] == launched
+        for pos_rule in (0, 1):  # other second anchors
+            got = [ss.DynamicB200Searcher.with_position(w, min(pos_rule, len(w) - 1)).find_in(hs) for w in sample[:40]]
+            assert got == launched[:40]
+        time.sleep(0.01)  # longer than the idle time: the grid retires and the next call starts a new one
+    served = 3 * (len(sample) + 80)
+    assert ss.launch_count() - l0 < served // 4, "most synchronous calls must not launch anything"
+    # the haystack changes between calls: the resident grid must see the new bytes (no stale L1 lines)
+    t = torch.frombuffer(bytearray(i386[:300000]), dtype=torch.uint8).cuda()
+    s = ss.DynamicB200Searcher.new(b"\x01\x02needle\x03")
+    assert s.find_in(t) is None
+    for spot in (299990, 150001, 77, 0):
+        t[spot:spot + 9] = torch.tensor(list(b"\x01\x02needle\x03"), dtype=torch.uint8, device="cuda")
+        assert s.find_in(t) == spot
+    # unaligned views, tiny haystacks, needle == haystack
+    for shift in (0, 1, 7, 15):
+        for n in (1, 2, 9, 16, 17, 31, 33, 100, 4097):
+            v = t[shift:shift + n]
+            hb = bytes(v.cpu().numpy())
+            for nd in (hb[:1], hb[-2:], hb[n // 2:n // 2 + 5], hb, b"\xfe\xfd"):
+                if not nd:
+                    continue
+                e = hb.find(nd)
+                assert ss.DynamicB200Searcher.new(nd).find_in(v) == (None if e < 0 else e), (shift, n, nd)
+    # more threads than service slots per device: the extra ones launch kernels, answers stay the same
+    errs = []
+
+    def work(idx):
+        try:
+            for rep in range(20):
+                for w, e in list(zip(sample, launched))[idx::8]:
+                    assert ss.DynamicB200Searcher.new(w).find_in(hs) == e
+            ss.thread_release()  # with a grid resident
+        except Exception as ex:  # noqa: BLE001
+            errs.append(repr(ex))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    # implicit synchronisations (cudaFree inside close()) only wait for the idle time
+    t0 = time.perf_counter()
+    assert searchers[0].find_in(hs) == launched[0]
+    hs2 = ss.DeviceHaystack.upload(i386[:4096])
+    hs2.close()
+    assert time.perf_counter() - t0 < 1.0
+    ss.thread_release()
+    assert searchers[1].find_in(hs) == launched[1]  # rebuilt on demand
+
+
 def test_peer_exchange_world1_mailbox_kernels():
     """ss_b200_find_in_device_exchange_async with world == 1: the scan's epilogue posts into the rank's
     own mailbox and mailbox_min_kernel collects it -- the whole fused-exchange code path on one GPU."""
