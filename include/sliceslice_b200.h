@@ -400,7 +400,7 @@ int ss_b200_set_launch_pdl(int on);
  * exit.  on = 0: always launch (idle_us == 0 keeps the current value). */
 int ss_b200_set_sync_service(int on, int idle_us);
 /* Host-slice path (ss_b200_find_in_host / _multi):
- *   mode          0 auto (pinned slices up to 16 MiB in place, else the DMA ring), 1 always the DMA ring,
+ *   mode          0 auto (pinned slices of up to 2 MiB per device in place, else the DMA ring), 1 always the DMA ring,
  *                 2 pinned input read in place by the direct-load kernel, 3 in place by the TMA kernel
  *   chunk_mib     0 auto (an eighth of a device's share of the slice, 4..64 MiB), else MiB per chunk
  *   copy_threads  memcpy workers that stage pageable input: -1 auto (min(7, cores-1); 15 for a

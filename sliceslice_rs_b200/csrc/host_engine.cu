@@ -196,9 +196,11 @@ int ensure_chunk_results(SsLane *c, size_t n)
     return SS_B200_OK;
 }
 
-// in-place auto mode: pinned slices up to this size are read over PCIe by the scan itself
-// (profiles/r02_host_path.txt: below it the single launch beats the copy/scan pipeline's ramp)
-constexpr size_t SS_INPLACE_AUTO_MAX = (size_t)16 << 20;
+// in-place auto mode: pinned slices of up to this many bytes PER LANE are read over PCIe by the scan itself.
+// Measured (profiles/r02_host_path_n1.json, _n8.json): one launch per lane beats the copy/scan ring's ramp
+// below ~2 MiB per device (1 MiB on one GPU: 26.4 vs 23.5 GB/s; 16 MiB over eight: 131 vs 93 GB/s); from
+// 16 MiB per device on, the DMA ring wins (49.7 vs 47.8, 55.3 vs 50.2 GB/s).
+constexpr size_t SS_INPLACE_AUTO_MAX_PER_LANE = (size_t)2 << 20;
 
 } // namespace
 
@@ -245,7 +247,7 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searche
     if (mode >= 2 && !(pinned && dev_view))
         mode = 1; // nothing to read in place: the device cannot address this memory
     if (mode == 0)
-        mode = (pinned && dev_view && len <= SS_INPLACE_AUTO_MAX) ? 2 : 1;
+        mode = (pinned && dev_view && len <= SS_INPLACE_AUTO_MAX_PER_LANE * (size_t)n_lanes) ? 2 : 1;
     const bool inplace = mode >= 2;
 
     int pool_threads = 0;
