@@ -7,7 +7,7 @@ cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 O=gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $O/gpu.txt 2>&1
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "histogram or kats or edge" > $O/pytest_new.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_ctx.py -x -q -m gpu > $O/pytest_new.log 2>&1
 echo "pytest_new rc=$?" >> $O/steps.log
 timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 echo "bench rc=$?" >> $O/steps.log
