@@ -477,6 +477,7 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         if it:
             ebest = dt if ebest is None else min(ebest, dt)
     assert int(o3.sum()) == 809985317
+    cpp_host = compiled_host_literal_loop()
     out["config2_literal"] = {
         "e2e_host_buffers_ms_per_iteration": round(ebest * 1e3, 3),
         "what": "all 4585 words.txt needles over the 857425-byte i386.txt, device-resident, host wall clock",
@@ -484,6 +485,7 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         "api_faithful_how": "one synchronous ss_b200_find_in per needle; short device-resident haystacks are served by "
                             "a resident kernel (one PCIe round trip per call, no launch)",
         "api_faithful_one_launch_per_call_ms": sync_ms["one_launch_per_call"],
+        "api_faithful_compiled_host": cpp_host,
         "api_faithful_async_ms_per_iteration": round(abest * 1e3, 3),
         "batched_single_launch_ms_per_iteration": round(bbest * 1e3, 3),
         "examined_bytes": 810016020, "sum_first_offsets": 809985317,
@@ -562,6 +564,39 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
         "grid_x1000_in_one_launch_ns_per_search": round(tk * 1e9 / pn_k.size, 3),
     }
     return out
+
+
+def compiled_host_literal_loop():
+    """The same per-needle loop from a COMPILED host (tests/cpp/bench_latency.cpp through the C++ mirror), the
+    way the reference's own bench calls it from Rust: what a call costs without the Python interpreter
+    around it.  Built with g++ on the spot; None if that is not possible."""
+    try:
+        import re
+
+        import sliceslice_rs_b200 as ss
+
+        build_dir = os.path.join(ROOT, "tests", "cpp", "_build")
+        os.makedirs(build_dir, exist_ok=True)
+        exe = os.path.join(build_dir, "bench_latency")
+        lib_dir = os.path.dirname(ss.LIB_PATH)
+        cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+               os.path.join(ROOT, "tests", "cpp", "bench_latency.cpp"), "-o", exe, ss.LIB_PATH,
+               "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64"]
+        subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=120)
+        res = {}
+        for label, flag in (("resident_service_kernel_ms", "1"), ("one_launch_per_call_ms", "0")):
+            r = subprocess.run([exe, os.path.join(ROOT, "data", "i386.txt"), os.path.join(ROOT, "data", "words.txt"), flag],
+                               capture_output=True, text=True, timeout=300)
+            sync = [float(x) for x in re.findall(r"one find_in per word, device haystack\): ([0-9.]+) ms/iteration", r.stdout)]
+            asyn = [float(x) for x in re.findall(r"one find_in_device_async per word, one sync\): ([0-9.]+) ms/iteration", r.stdout)]
+            if not sync or "sum 809985317" not in r.stdout:
+                return None
+            res[label] = round(min(sync), 3)
+            res["stream_ordered_ms"] = round(min(asyn), 3) if asyn else None
+        res["what"] = "tests/cpp/bench_latency.cpp: one synchronous find_in per needle from C++ (best of 4 iterations)"
+        return res
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def random_grid():

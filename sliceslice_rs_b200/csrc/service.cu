@@ -23,10 +23,10 @@
 #include <atomic>
 #include <cstring>
 
-#define SS_SERVICE_THREADS 512
+#define SS_SERVICE_THREADS 256
 #define SS_SERVICE_MAX_BYTES ((size_t)4 << 20)
 #define SS_SERVICE_MAX_NEEDLE 64u
-#define SS_SERVICE_MAX_PER_DEVICE 2
+#define SS_SERVICE_MAX_PER_DEVICE 4
 
 // request, 128 bytes of mapped pinned host memory = two 64-byte lines, each closed by the request number
 struct SsServiceDesc {
@@ -133,97 +133,6 @@ __device__ __forceinline__ void service_scan(const ScanArgs &a)
     }
 }
 
-#define SS_SERVICE_POLL_WARPS 4
-
-// CTA 0, warps 0 .. SS_SERVICE_POLL_WARPS-1: wait for the next request in the host's mapped memory.
-// Every warp polls on its own (one coalesced 128-byte PCIe read per iteration; their phases drift apart, so
-// a new request is seen after about one read instead of one and a half); the first warp to see it claims it
-// (shared-memory CAS), publishes it to the other CTAs and raises `s_ready`; the others wait for that.
-// Warp 0 also retires the grid when no request has come for idle_ns.  On return s_seq holds the request
-// number, or 0xFFFFFFFF to leave, and s_desc the request.  Every branch below is warp-uniform.
-__device__ __forceinline__ void leader_wait(SsServiceCtl *ctl, const uint32_t *host_desc, SsServiceStatus *status,
-                                            unsigned int last, unsigned long long idle_ns, unsigned int epoch,
-                                            unsigned long long t_idle, int warp, int lane, uint32_t *s_desc,
-                                            unsigned int *s_claim, volatile unsigned int *s_ready, unsigned int *s_seq)
-{
-    for (;;) {
-        if (*s_ready)
-            return;
-        uint32_t v = ld_sys_u32(host_desc + lane);
-        uint32_t seq0 = __shfl_sync(0xFFFFFFFFu, v, 0), seq1 = __shfl_sync(0xFFFFFFFFu, v, 31);
-        bool fresh = seq0 == seq1 && seq0 != last && seq0 != 0u;
-        bool retire = false;
-        if (!fresh && warp == 0) {
-            const unsigned long long now = __shfl_sync(0xFFFFFFFFu, now_ns(), 0);
-            retire = now - t_idle > idle_ns;
-        }
-        if (!fresh && !retire)
-            continue;
-        unsigned int won = 0;
-        if (lane == 0)
-            won = atomicCAS(s_claim, 0u, 1u) == 0u ? 1u : 0u;
-        won = __shfl_sync(0xFFFFFFFFu, won, 0);
-        if (!won) { // another warp is on it: wait for its verdict
-            while (!*s_ready) {
-            }
-            return;
-        }
-        if (!fresh) {
-            // retire: say so FIRST, then look once more -- the host writes its request and then reads
-            // `alive`, so either we see the request here or the host sees alive == 0
-            if (lane == 0)
-                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&status->alive), "r"(0u) : "memory");
-            __threadfence_system();
-            __syncwarp();
-            v = ld_sys_u32(host_desc + lane);
-            seq0 = __shfl_sync(0xFFFFFFFFu, v, 0);
-            seq1 = __shfl_sync(0xFFFFFFFFu, v, 31);
-            fresh = seq0 == seq1 && seq0 != last && seq0 != 0u;
-            if (!fresh) {
-                if (lane == 0) {
-                    st_release_u32(&ctl->exit_epoch, epoch);
-                    *s_seq = 0xFFFFFFFFu;
-                    __threadfence_block();
-                    *s_ready = 1u;
-                }
-                return;
-            }
-            if (lane == 0) // a request slipped in: stay and serve it
-                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&status->alive), "r"(1u) : "memory");
-        }
-        const uint32_t cmd = __shfl_sync(0xFFFFFFFFu, v, 3);
-        if (cmd == 2u) { // retire on request
-            if (lane == 0) {
-                ctl->served = seq0;
-                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&status->alive), "r"(0u) : "memory");
-                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&status->result), "l"(SS_NONE_U64) : "memory");
-                st_release_u32(&ctl->exit_epoch, epoch);
-                *s_seq = 0xFFFFFFFFu;
-            }
-        } else {
-            // publish: the request and a fresh reduction state, then (release) its number
-            ctl->desc[lane] = v;
-            if (lane == 0) {
-                ctl->ws.key = 0ull;
-                ctl->ws.done = 0u;
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                st_release_u32(&ctl->go, seq0);
-                *s_seq = seq0;
-            }
-            s_desc[lane] = v;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            *s_ready = 1u;
-        }
-        return;
-    }
-}
-
 __global__ void __launch_bounds__(SS_SERVICE_THREADS, 1)
     service_kernel(SsServiceCtl *ctl, const uint32_t *host_desc, SsServiceStatus *status, unsigned long long idle_ns,
                    unsigned int epoch)
@@ -231,43 +140,88 @@ __global__ void __launch_bounds__(SS_SERVICE_THREADS, 1)
     __shared__ ScanArgs sa;
     __shared__ uint32_t s_desc[32];
     __shared__ unsigned int s_seq;
-    __shared__ unsigned int s_claim;
-    __shared__ unsigned int s_ready;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const bool leader_cta = blockIdx.x == 0;
     unsigned int last = ld_gpu_u32(&ctl->served); // requests up to here are history
     unsigned long long t_idle = now_ns();
     const unsigned long long watchdog_ns = 8ull * idle_ns + 200000000ull; // a CTA never spins longer than this
-    if (threadIdx.x == 0) {
-        s_claim = 0u;
-        s_ready = 0u;
-    }
-    __syncthreads();
 
     for (;;) {
-        // ---- wait for the next request ----
-        if (leader_cta) {
-            if (warp < SS_SERVICE_POLL_WARPS)
-                leader_wait(ctl, host_desc, status, last, idle_ns, epoch, t_idle, warp, lane, s_desc, &s_claim, &s_ready,
-                            &s_seq);
-        } else if (threadIdx.x < 32) {
+        // ---- wait for the next request (warp 0; every decision below is warp-uniform) ----
+        if (threadIdx.x < 32) {
             unsigned int got = 0;
-            const unsigned long long t0 = __shfl_sync(0xFFFFFFFFu, now_ns(), 0);
-            for (;;) {
-                // every lane polls (one broadcast transaction), so every lane has acquired what it reads next
-                const unsigned int g = __shfl_sync(0xFFFFFFFFu, ld_acquire_u32(&ctl->go), 0);
-                if (g != last) {
-                    (void)ld_acquire_u32(&ctl->go);
-                    s_desc[lane] = ld_gpu_u32(ctl->desc + lane); // from L2, never L1: rewritten per request
-                    got = g;
-                    break;
+            if (leader_cta) {
+                for (;;) {
+                    const uint32_t v = ld_sys_u32(host_desc + lane); // one 128-byte read over PCIe
+                    uint32_t seq0 = __shfl_sync(0xFFFFFFFFu, v, 0), seq1 = __shfl_sync(0xFFFFFFFFu, v, 31);
+                    if (seq0 == seq1 && seq0 != last && seq0 != 0u) {
+                        const uint32_t cmd = __shfl_sync(0xFFFFFFFFu, v, 3);
+                        if (cmd == 2u) { // retire on request
+                            if (lane == 0) {
+                                ctl->served = seq0;
+                                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&status->alive), "r"(0u) : "memory");
+                                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&status->result), "l"(SS_NONE_U64)
+                                             : "memory");
+                                st_release_u32(&ctl->exit_epoch, epoch);
+                            }
+                            got = 0xFFFFFFFFu;
+                            break;
+                        }
+                        // publish: the request and a fresh reduction state, then (release) its number
+                        ctl->desc[lane] = v;
+                        if (lane == 0) {
+                            ctl->ws.key = 0ull;
+                            ctl->ws.done = 0u;
+                        }
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0)
+                            st_release_u32(&ctl->go, seq0);
+                        s_desc[lane] = v;
+                        got = seq0;
+                        break;
+                    }
+                    const unsigned long long now = __shfl_sync(0xFFFFFFFFu, now_ns(), 0);
+                    if (now - t_idle > idle_ns) {
+                        // retire: say so FIRST, then look once more -- the host writes its request and then
+                        // reads `alive`, so either we see the request here or the host sees alive == 0
+                        if (lane == 0)
+                            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&status->alive), "r"(0u) : "memory");
+                        __threadfence_system();
+                        __syncwarp();
+                        const uint32_t v2 = ld_sys_u32(host_desc + lane);
+                        seq0 = __shfl_sync(0xFFFFFFFFu, v2, 0);
+                        seq1 = __shfl_sync(0xFFFFFFFFu, v2, 31);
+                        if (seq0 == seq1 && seq0 != last && seq0 != 0u) {
+                            if (lane == 0)
+                                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&status->alive), "r"(1u)
+                                             : "memory");
+                            t_idle = now;
+                            continue; // picked up at the top of the loop
+                        }
+                        if (lane == 0)
+                            st_release_u32(&ctl->exit_epoch, epoch);
+                        got = 0xFFFFFFFFu;
+                        break;
+                    }
                 }
-                const unsigned int ex = __shfl_sync(0xFFFFFFFFu, ld_gpu_u32(&ctl->exit_epoch), 0);
-                const unsigned long long now = __shfl_sync(0xFFFFFFFFu, now_ns(), 0);
-                if (ex == epoch || now - t0 > watchdog_ns) {
-                    got = 0xFFFFFFFFu;
-                    break;
+            } else {
+                const unsigned long long t0 = __shfl_sync(0xFFFFFFFFu, now_ns(), 0);
+                for (;;) {
+                    // every lane polls (one broadcast transaction), so every lane has acquired what it reads next
+                    const unsigned int g = __shfl_sync(0xFFFFFFFFu, ld_acquire_u32(&ctl->go), 0);
+                    if (g != last) {
+                        (void)ld_acquire_u32(&ctl->go);
+                        s_desc[lane] = ld_gpu_u32(ctl->desc + lane); // from L2, never L1: rewritten per request
+                        got = g;
+                        break;
+                    }
+                    const unsigned int ex = __shfl_sync(0xFFFFFFFFu, ld_gpu_u32(&ctl->exit_epoch), 0);
+                    const unsigned long long now = __shfl_sync(0xFFFFFFFFu, now_ns(), 0);
+                    if (ex == epoch || now - t0 > watchdog_ns) {
+                        got = 0xFFFFFFFFu;
+                        break;
+                    }
                 }
             }
             if (lane == 0)
@@ -279,10 +233,6 @@ __global__ void __launch_bounds__(SS_SERVICE_THREADS, 1)
             return;
 
         // ---- kernel arguments of this search, as ss_capi_build_args + ss_host_scan_geometry make them ----
-        if (threadIdx.x == 0) { // nobody looks at these two between the barrier above and the next wait
-            s_claim = 0u;
-            s_ready = 0u;
-        }
         if (threadIdx.x < 32) {
             const uint8_t *nb = reinterpret_cast<const uint8_t *>(s_desc + 8); // needle bytes 0..63
             if (lane == 0) {
