@@ -481,12 +481,16 @@ def extras_single_gpu(ss, torch, i386: bytes, hay, args):
     out["config2_literal"] = {
         "e2e_host_buffers_ms_per_iteration": round(ebest * 1e3, 3),
         "what": "all 4585 words.txt needles over the 857425-byte i386.txt, device-resident, host wall clock",
-        "api_faithful_ms_per_iteration": round(best * 1e3, 3),
+        # the loop of bench/benches/i386.rs:252-256 is compiled code on both sides: the headline figure is the
+        # compiled C++ host's (tests/cpp/bench_latency.cpp); the same loop driven from Python is beside it
+        "api_faithful_ms_per_iteration": ((cpp_host or {}).get("resident_service_kernel_ms") or round(best * 1e3, 3)),
         "api_faithful_how": "one synchronous ss_b200_find_in per needle; short device-resident haystacks are served by "
                             "a resident kernel (one PCIe round trip per call, no launch)",
-        "api_faithful_one_launch_per_call_ms": sync_ms["one_launch_per_call"],
         "api_faithful_compiled_host": cpp_host,
-        "api_faithful_async_ms_per_iteration": round(abest * 1e3, 3),
+        "api_faithful_python_ctypes_ms": round(best * 1e3, 3),
+        "api_faithful_python_ctypes_one_launch_per_call_ms": sync_ms["one_launch_per_call"],
+        "api_faithful_async_ms_per_iteration": ((cpp_host or {}).get("stream_ordered_ms") or round(abest * 1e3, 3)),
+        "api_faithful_async_python_ctypes_ms": round(abest * 1e3, 3),
         "batched_single_launch_ms_per_iteration": round(bbest * 1e3, 3),
         "examined_bytes": 810016020, "sum_first_offsets": 809985317,
         "readme_i7_6700_ms": 35.181,

@@ -8,11 +8,9 @@ timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --mast
 echo "bench_n8 rc=$?" >> $O/steps.log
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus 8 --impl reference --steps 5 --warmup 1 > $O/bench_ref_n8.json 2> $O/bench_ref_n8.err
 echo "bench_ref8 rc=$?" >> $O/steps.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29553 bench.py --gpus 4 --steps 40 --no-extras > $O/bench_n4.json 2> $O/bench_n4.err
-echo "bench_n4 rc=$?" >> $O/steps.log
 cat $O/steps.log; head -c 400 $O/bench_n8.json; echo; python - <<'PY'
 import json
-for f in ("gpurun_out/bench_n8.json","gpurun_out/bench_n4.json"):
+for f in ("gpurun_out/bench_n8.json",):
     try:
         d=json.loads([l for l in open(f).read().split("\n") if l.startswith("{")][0])
         print(f, d["value"], d["ms_per_step"], d["e2e"]["value"], d["e2e"]["roofline"])
