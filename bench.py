@@ -71,7 +71,7 @@ def parse_args():
     p.add_argument("--mode", default="single", choices=["single", "many"],
                    help="single = one haystack sharded by start position (the headline); many = the batched "
                         "many-haystack mode: every GPU holds its own set of haystacks, per-haystack flags are "
-                        "OR-ed across GPUs with all_reduce(MAX)")
+                        "OR-ed across GPUs as a bit-packed bitmap (all_reduce(SUM) over disjoint bits)")
     p.add_argument("--sustained-steps", type=int, default=300,
                    help="a second, longer timed run for the sustained (power-capped) rate; 0 = skip")
     p.add_argument("--no-extras", action="store_true")

@@ -294,8 +294,10 @@ int ss_b200_ctx_hayset_search(ss_b200_ctx *ctx, const ss_b200_searcher *s, const
  *   d_offsets         n_haystacks+1 uint64 in device memory, d_offsets[0] == 0, d_offsets[n] == blob_len
  *   d_flags           n_haystacks uint8 in device memory: set to 1/0 per haystack
  *   workspace         32 bytes of device memory, zero when enqueued (left zero again)
- * Multi-GPU: each rank holds a subset of the haystacks and writes its slice of one global flag
- * array; the slices are OR-ed with ncclAllReduce(ncclMax, ncclUint8) (NCCL has no bitwise OR). */
+ * Multi-GPU, one process per GPU: each rank holds a subset of the haystacks, packs its flags into its
+ * bit range of one global bitmap (ss_b200_pack_flags_async) and the bitmaps are OR-ed with
+ * ncclAllReduce(ncclSum, ncclUint32) -- disjoint bits, and NCCL has no bitwise OR.  One process, all GPUs:
+ * ss_b200_ctx_hayset_search gathers the disjoint flag slices. */
 int ss_b200_search_many_async(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets,
                               size_t n_haystacks, size_t blob_len, uint8_t *d_flags, void *workspace, void *stream);
 

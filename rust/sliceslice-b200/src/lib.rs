@@ -60,6 +60,7 @@ extern "C" {
     fn ss_b200_search_in_host(s: *const RawSearcher, host: *const u8, len: usize, found: *mut u8) -> c_int;
     fn ss_b200_find_in_host(s: *const RawSearcher, host: *const u8, len: usize, offset: *mut usize) -> c_int;
     fn ss_b200_thread_release() -> c_int;
+    fn ss_b200_set_sync_service(on: c_int, idle_us: c_int) -> c_int;
     // multi-GPU context (one process, every GPU of the box)
     fn ss_b200_ctx_create(ndev: c_int, devices: *const c_int, out: *mut *mut RawCtx) -> c_int;
     fn ss_b200_ctx_free(ctx: *mut RawCtx);
@@ -81,6 +82,12 @@ extern "C" {
     fn ss_b200_ctx_hayset_free(hs: *mut RawCtxHayset);
     fn ss_b200_ctx_hayset_len(hs: *const RawCtxHayset) -> usize;
     fn ss_b200_ctx_hayset_search(ctx: *mut RawCtx, s: *const RawSearcher, hs: *const RawCtxHayset, flags: *mut u8) -> c_int;
+}
+
+/// Synchronous searches over short device-resident haystacks go through a resident kernel (no launch per
+/// call) by default; `false` launches a kernel per call.  `idle_us == 0` keeps the current idle time.
+pub fn set_sync_service(on: bool, idle_us: u32) {
+    check(unsafe { ss_b200_set_sync_service(on as c_int, idle_us as c_int) });
 }
 
 /// Frees the calling thread's streams, result slot and staging ring (they are also freed at thread exit).

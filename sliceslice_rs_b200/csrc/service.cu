@@ -27,6 +27,10 @@
 #define SS_SERVICE_MAX_BYTES ((size_t)4 << 20)
 #define SS_SERVICE_MAX_NEEDLE 64u
 #define SS_SERVICE_MAX_PER_DEVICE 4
+#ifndef SS_SERVICE_GRID_NUM // CTAs of the resident grid = SMs * NUM / DEN
+#define SS_SERVICE_GRID_NUM 1
+#define SS_SERVICE_GRID_DEN 1
+#endif
 
 // request, 128 bytes of mapped pinned host memory = two 64-byte lines, each closed by the request number
 struct SsServiceDesc {
@@ -462,7 +466,7 @@ int ss_service_find(SsLane *lane, const ss_b200_searcher *s, const void *dptr, s
         int rc = ss_capi_device_info(dev);
         cudaError_t e = cudaSuccess;
         if (rc == SS_B200_OK) {
-            sv->grid = dev.sm_count;
+            sv->grid = dev.sm_count * SS_SERVICE_GRID_NUM / SS_SERVICE_GRID_DEN;
             e = cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking);
         }
         if (rc == SS_B200_OK && e == cudaSuccess)

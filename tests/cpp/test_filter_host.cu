@@ -55,7 +55,7 @@ static bool run_case(const Case &t, const std::vector<long long> &truth)
         const uint4 hi = (K1 || q == 0) ? nx : load_chunk(t.base, c + q + 1 < last ? c + q + 1 : last);
         const uint32_t flag_plain = chunk_flag_x<WS, BSZ, K1, 0>(av, nx, lo, hi, fc);
         const uint32_t flag_extra = chunk_flag_x<WS, BSZ, K1, XK>(av, nx, lo, hi, fc);
-        // hit path, as verify_chunk
+        // hit path, as step_alive_mask + hit_tail
         std::vector<long long> here;
         uint32_t z[4] = {0, 0, 0, 0};
         const bool alive = exact_alive<WS, BSZ, K1>(av, nx, lo, hi, fc, t.k,
