@@ -395,7 +395,7 @@ int ss_b200_set_extra_anchors(int n);
 int ss_b200_set_launch_pdl(int on);
 /* Synchronous searches (ss_b200_find_in / ss_b200_search_in) over device-resident haystacks of up to
  * 4 MiB with needles of up to 64 bytes do not launch a kernel per call: a resident grid per calling thread
- * (at most four per device) polls a request word in mapped pinned memory and answers into another, so a
+ * (at most two per device) polls a request word in mapped pinned memory and answers into another, so a
  * call costs one PCIe round trip plus the scan -- the regime of the reference's per-needle loops
  * (bench/benches/i386.rs:252-256).  The grid retires by itself idle_us after the last call (default 100;
  * implicit synchronisations such as cudaFree wait at most that long) and at ss_b200_thread_release / thread

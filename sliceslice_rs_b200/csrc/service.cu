@@ -26,9 +26,9 @@
 #define SS_SERVICE_THREADS 256
 #define SS_SERVICE_MAX_BYTES ((size_t)4 << 20)
 #define SS_SERVICE_MAX_NEEDLE 64u
-#define SS_SERVICE_MAX_PER_DEVICE 4
+#define SS_SERVICE_MAX_PER_DEVICE 2
 #ifndef SS_SERVICE_GRID_NUM // CTAs of the resident grid = SMs * NUM / DEN
-#define SS_SERVICE_GRID_NUM 1
+#define SS_SERVICE_GRID_NUM 2
 #define SS_SERVICE_GRID_DEN 1
 #endif
 
@@ -137,7 +137,7 @@ __device__ __forceinline__ void service_scan(const ScanArgs &a)
     }
 }
 
-__global__ void __launch_bounds__(SS_SERVICE_THREADS, 1)
+__global__ void __launch_bounds__(SS_SERVICE_THREADS, 4)
     service_kernel(SsServiceCtl *ctl, const uint32_t *host_desc, SsServiceStatus *status, unsigned long long idle_ns,
                    unsigned int epoch)
 {
