@@ -153,7 +153,7 @@ struct SsHostStats {
     unsigned long long chunk_bytes = 0;
 };
 int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searcher *s, const uint8_t *host, size_t len,
-                        size_t *offset, SsHostStats *stats);
+                        size_t *offset, SsHostStats *stats); // (pageable input: staged through ONE lane's pinned ring)
 
 // many-haystack scan shared by ss_b200_search_many_async (no hints) and ss_b200_hayset_search_async
 int ss_capi_search_many(const ss_b200_searcher *s, const void *d_blob, const uint64_t *d_offsets, size_t n_haystacks,

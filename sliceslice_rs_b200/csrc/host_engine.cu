@@ -204,11 +204,12 @@ constexpr size_t SS_INPLACE_AUTO_MAX_PER_LANE = (size_t)2 << 20;
 
 } // namespace
 
-int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searcher *s, const uint8_t *host, size_t len,
-                        size_t *offset, SsHostStats *stats)
+int ss_host_engine_find(SsLane *const *lanes, int n_lanes_in, const ss_b200_searcher *s, const uint8_t *host,
+                        size_t len, size_t *offset, SsHostStats *stats)
 {
-    if (!s || !offset || !lanes || n_lanes < 1 || (len && !host))
+    if (!s || !offset || !lanes || n_lanes_in < 1 || (len && !host))
         return SS_B200_E_ARG;
+    int n_lanes = n_lanes_in;
     SsHostStats st_local;
     SsHostStats &st = stats ? *stats : st_local;
     st = SsHostStats();
@@ -256,14 +257,20 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes, const ss_b200_searche
         int want = ht.copy_threads;
         if (want < 0) {
             const unsigned hc = std::thread::hardware_concurrency();
-            const unsigned cap = n_lanes > 1 ? 15u : 7u; // workers next to the calling thread
-            want = hc > 2 ? (int)(hc - 1 < cap ? hc - 1 : cap) : 0;
+            want = hc > 2 ? (int)(hc - 1 < 7u ? hc - 1 : 7u) : 0; // workers next to the calling thread
         }
         if (want > 0) {
             pool_threads = CopyPool::get().ensure(want);
             pool_threads = pool_threads < want ? pool_threads : want;
             staged = true;
         }
+    }
+    if (staged) {
+        // Pageable input is bound by the staging memcpy (the host's DRAM read + write), not by a PCIe link:
+        // one device drains the pinned ring as fast as the pool fills it, and more lanes only cut the slice
+        // into smaller chunks (measured on 8 x B200, 1 GiB pageable: 49 GB/s over one device, 42 / 39 / 34
+        // over 2 / 4 / 8; profiles/r02_host_path_n8.json).
+        n_lanes = 1;
     }
 
     const size_t halo = k - 1;

@@ -80,7 +80,8 @@ __device__ __forceinline__ FilterConsts load_filter_consts(const ScanArgs &a)
 // Returns true when the early-exit test says this CTA can stop.
 template <int WS, bool BSZ, bool QZ, bool K1, int XK, int U, bool CLAMP>
 __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restrict__ chunks, unsigned long long cw,
-                                         int lane, const FilterConsts &fc, AdaptiveFilter &af, uint32_t &occ)
+                                         int lane, const FilterConsts &fc, AdaptiveFilter &af, uint32_t &occ,
+                                         bool look_left)
 {
     // early exit: nothing at or right of this warp's first position can beat the current best
     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
@@ -130,7 +131,7 @@ __device__ __forceinline__ bool ldg_step(const ScanArgs &a, const uint4 *__restr
         // soon as any lane's reading says so; the vote keeps the decision warp-uniform whatever each
         // lane's load returned
         const long long first_pos = (long long)(cw * 16ull) - (long long)a.head;
-        if (__any_sync(0xFFFFFFFFu, (key != 0 && first_pos > (long long)~key) || peer_stop_requested(a)))
+        if (__any_sync(0xFFFFFFFFu, (key != 0 && first_pos > (long long)~key) || (look_left && peer_stop_requested(a))))
             return true;
     }
     uint32_t fl[U];
@@ -191,13 +192,15 @@ __global__ void __launch_bounds__(SS_LDG_THREADS) scan_ldg_kernel(const __grid_c
 
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long cw = tile * CTA_CHUNKS + (unsigned long long)warp * (U * 32);
+        // the stop word of a sharded search is looked at every eighth tile of the CTA
+        const bool look_left = ((tile / gridDim.x) & 7ull) == 0ull;
         bool stop;
         if (tile < n_interior) {
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af, occ);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, false>(a, chunks, cw, lane, fc, af, occ, look_left);
         } else {
             if (cw >= a.n_chunks)
                 continue; // this warp's run holds no start position (warp-uniform)
-            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af, occ);
+            stop = ldg_step<WS, BSZ, QZ, K1, XK, U, true>(a, chunks, cw, lane, fc, af, occ, look_left);
         }
         if (stop)
             break; // every later tile of this CTA is further right still
@@ -319,7 +322,8 @@ __global__ void __launch_bounds__(SS_TMA_THREADS, 2)
                 if (go) {
                     const unsigned long long key = ld_relaxed_u64(&a.ws->key);
                     const long long first_pos = (long long)(tile * (unsigned long long)TILE) - (long long)a.head;
-                    if ((key && first_pos > (long long)~key) || peer_stop_requested(a))
+                    // (the stop word of a sharded search is looked at every eighth tile of the CTA)
+                    if ((key && first_pos > (long long)~key) || (((tile / gridDim.x) & 7ull) == 0ull && peer_stop_requested(a)))
                         go = false;
                 }
                 if (!go) {

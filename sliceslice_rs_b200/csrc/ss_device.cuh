@@ -103,13 +103,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 #include "ss_filter.cuh"
 
 // Has a shard to the left already matched (see ScanArgs::stop_word)?  Launch-uniform branch on the pointer.
+// The word lives in THIS GPU's memory; peers store into it over NVLink, which lands in this GPU's L2 -- so a
+// gpu-scope load (what `key` is polled with) sees it.  Callers poll it every few tiles only: the first
+// version polled it with a sys-scope load before every tile and cost the sharded scan 3-4 %
+// (1.296 vs 1.247 ms per 8 GiB search, profiles/r02_bench_n2.json).
 __device__ __forceinline__ bool peer_stop_requested(const ScanArgs &a)
 {
     if (a.stop_word == nullptr)
         return false;
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.stop_word) : "memory");
-    return v == a.stop_seq;
+    return ld_relaxed_u64(a.stop_word) == a.stop_seq;
 }
 
 // Per-warp, per-tile switch between the plain two-anchor filter and the one with extra anchors.
