@@ -157,3 +157,59 @@ def test_rarest_position_default_table_prefers_unusual_bytes():
     with pytest.raises(ss.SearcherPanic):
         ss.B200Searcher.with_rarest_position(b"")  # Avx2Searcher::new(empty) panics, src/x86.rs:285,300
     assert ss.DynamicB200Searcher.with_rarest_position(b"").search_in(b"") is True
+
+
+# ---- round 2's boundary additions: everything that can be pinned without a device -----------------
+
+def test_setters_validate_their_arguments():
+    L = ss.lib()
+    assert L.ss_b200_set_host_path(0, 0, -1) == ss.OK
+    for bad in ((4, 0, -1), (-1, 0, -1), (0, -1, -1), (0, 5000, -1), (0, 0, -2), (0, 0, 1000)):
+        assert L.ss_b200_set_host_path(*bad) == ss.E_ARG, bad
+    assert L.ss_b200_set_launch_pdl(2) == ss.E_ARG and L.ss_b200_set_launch_pdl(1) == ss.OK
+    assert L.ss_b200_set_sync_service(2, 0) == ss.E_ARG and L.ss_b200_set_sync_service(1, -5) == ss.E_ARG
+    assert L.ss_b200_set_sync_service(1, 0) == ss.OK
+    assert L.ss_b200_set_scan_variant(3) == ss.E_ARG and L.ss_b200_set_scan_variant(0) == ss.OK
+    assert L.ss_b200_strerror(ss.E_NCCL).decode().lower().startswith("nccl")
+
+
+def test_no_environment_knobs_in_the_library():
+    # the reference reads no runtime configuration; every knob here is a ss_b200_set_* call
+    csrc = os.path.join(ROOT, "sliceslice_rs_b200", "csrc")
+    for f in os.listdir(csrc):
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+
+
+def test_nccl_is_loaded_on_demand_not_linked():
+    import subprocess
+
+    needed = subprocess.run(["readelf", "-d", ss.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in needed.lower()  # dlopen at ss_b200_ctx_set_exchange(NCCL), SS_B200_E_NCCL if absent
+    v = ss.nccl_version()  # the image has libnccl.so.2: loadable without a device
+    assert v >= 20000
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a machine without a GPU")
+def test_context_fails_loudly_without_gpu():
+    with pytest.raises(ss.B200Error):
+        ss.Context()
+    with pytest.raises(ss.B200Error):
+        ss.measure_h2d(1 << 20, 1)
+    # thread bookkeeping works without a device: nothing held, nothing to release
+    assert ss.thread_footprint() == (0, 0)
+    ss.thread_release()
+
+
+def test_thread_local_lanes_are_released_without_a_device():
+    import threading
+
+    out = []
+
+    def work():
+        out.append(ss.thread_footprint())
+        ss.thread_release()
+
+    t = threading.Thread(target=work)
+    t.start()
+    t.join()
+    assert out == [(0, 0)]
