@@ -623,10 +623,10 @@ extern "C" int ss_b200_count_in_device_async(const ss_b200_searcher *s, const vo
 
 // One synchronous scan of device-visible memory on a given lane (its device is made current for the call).
 int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                         int force_variant, bool plain_device_memory)
+                         int force_variant, int plain_device)
 {
     SsDeviceGuard guard(c->device);
-    if (plain_device_memory && force_variant == 0 && ss_service_eligible(s, len)) {
+    if (plain_device == c->device && force_variant == 0 && ss_service_eligible(s, len)) {
         // short device-resident haystack: through the resident kernel, no launch (service.cu)
         int on = 0;
         unsigned idle_us = 0;
@@ -663,7 +663,7 @@ int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr,
 
 // One synchronous scan of device memory through the calling thread's lane.
 int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                             int force_variant, bool plain_device_memory)
+                             int force_variant, int plain_device)
 {
     const size_t k = s->needle.size();
     if (k == 0) { // DynamicAvx2Searcher::N0 => true, even for an empty haystack (src/x86.rs:470,500)
@@ -680,14 +680,14 @@ int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t
     int rc = ss_capi_get_lane(&c);
     if (rc != SS_B200_OK)
         return rc;
-    return ss_capi_find_on_lane(c, s, dptr, len, offset, force_variant, plain_device_memory);
+    return ss_capi_find_on_lane(c, s, dptr, len, offset, force_variant, plain_device);
 }
 
 extern "C" int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t *offset)
 {
     if (!s || !h || !offset)
         return SS_B200_E_ARG;
-    return ss_capi_find_device_sync(s, h->dptr, h->len, offset, 0, h->plain_device_memory);
+    return ss_capi_find_device_sync(s, h->dptr, h->len, offset, 0, h->plain_device_memory ? h->device : -1);
 }
 
 extern "C" int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haystack *h, uint8_t *found)
@@ -695,7 +695,7 @@ extern "C" int ss_b200_search_in(const ss_b200_searcher *s, const ss_b200_haysta
     if (!s || !h || !found)
         return SS_B200_E_ARG;
     size_t off = SS_B200_NPOS;
-    int rc = ss_capi_find_device_sync(s, h->dptr, h->len, &off, 0, h->plain_device_memory);
+    int rc = ss_capi_find_device_sync(s, h->dptr, h->len, &off, 0, h->plain_device_memory ? h->device : -1);
     if (rc == SS_B200_OK)
         *found = (off != SS_B200_NPOS) ? 1 : 0;
     return rc;

@@ -110,10 +110,12 @@ struct SsDeviceGuard {
 
 // one synchronous scan of device-visible memory through the calling thread's lane
 // (force_variant: 0 = the process-wide tuning, 1 / 2 = that scan variant for this call)
+// plain_device: ordinal of the device whose plain (cudaMalloc-style) memory dptr is, or -1 when that is
+// not known -- the resident service kernel only serves memory of the lane's own device
 int ss_capi_find_device_sync(const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                             int force_variant, bool plain_device_memory = false);
+                             int force_variant, int plain_device = -1);
 int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr, size_t len, size_t *offset,
-                         int force_variant, bool plain_device_memory = false);
+                         int force_variant, int plain_device = -1);
 // service.cu: the resident kernel of the synchronous short-haystack calls
 bool ss_service_eligible(const ss_b200_searcher *s, size_t len);
 int ss_service_find(SsLane *lane, const ss_b200_searcher *s, const void *dptr, size_t len, unsigned idle_us,
