@@ -100,14 +100,9 @@ cudaError_t ss_host_launch_scan(const ScanArgs &a_in, const SsScanTuning &t, con
 
     choose_extra_anchors(a, t.extra_anchors);
     const int xk = (int)a.xk;
-    {
-        // which needle bytes does the filter of this launch compare?  (count mode counts needles of up to
-        // three bytes straight from the filter words when that is all of them)
-        uint32_t covered = 1u | (1u << (a.pos < 31u ? a.pos : 31u));
-        if (xk == 3)
-            covered |= 1u << (a.xbs / 8u);
-        a.filter_is_exact = (a.k <= 3u && covered == (1u << a.k) - 1u) ? 1u : 0u;
-    }
+    // count mode counts needles of up to three bytes straight from the filter words when the anchors of this
+    // launch compare every needle byte
+    a.filter_is_exact = filter_covers_needle(a.k, a.pos, xk, a.xbs / 8u) ? 1u : 0u;
 
     int variant = t.variant;
     if (variant == 0)

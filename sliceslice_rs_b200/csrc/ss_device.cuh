@@ -248,16 +248,6 @@ static __device__ __noinline__ unsigned long long segment_hit(const ScanArgs &a,
     return e - a.k + 1;
 }
 
-// The 0x80-per-alive-position words of one chunk (exact_alive) as 16 bits, bit p <-> start position p.
-__device__ __forceinline__ uint32_t pack_alive16(const uint32_t (&z)[4])
-{
-    uint32_t b16 = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        b16 |= ((((z[j] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * j); // bits 0, 8, 16, 24 -> bits 0..3
-    return b16;
-}
-
 // Hit path of one warp step, part 1 (inlined; no memory access): the exact compare of every flagged
 // chunk of the lane out of its registers -- the ctz loop + memcmp of src/lib.rs:216-248 for 16 start
 // positions at once (exact_alive; needle bytes as constant-bank operands).  The lane already holds the 32

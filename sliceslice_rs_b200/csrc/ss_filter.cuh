@@ -141,3 +141,26 @@ SS_UNROLL
     }
     return any != 0;
 }
+
+// The 0x80-per-alive-position words of one chunk (exact_alive) as 16 bits, bit p <-> start position p.
+SS_HD uint32_t pack_alive16(const uint32_t (&z)[4])
+{
+    uint32_t b16 = 0;
+SS_UNROLL
+    for (int j = 0; j < 4; j++)
+        b16 |= ((((z[j] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * j); // bits 0, 8, 16, 24 -> bits 0..3
+    return b16;
+}
+
+// Do the anchors of a launch's filter -- needle[0], needle[pos] and, for extra-anchor kind 3, needle[xo] --
+// compare EVERY byte of a needle of length k?  Then a zero byte of the filter word is an occurrence, and
+// count mode may count needles of up to three bytes straight from the filter words (scan_long.cuh).
+SS_HD bool filter_covers_needle(uint32_t k, uint32_t pos, int xk, uint32_t xo)
+{
+    if (k == 0u || k > 3u)
+        return false;
+    uint32_t covered = 1u | (1u << (pos < 31u ? pos : 31u));
+    if (xk == 3)
+        covered |= 1u << (xo < 31u ? xo : 31u);
+    return covered == (1u << k) - 1u;
+}

@@ -17,6 +17,8 @@
 #include <random>
 #include <vector>
 
+static long long g_exact_filter_chunks = 0; // chunks whose occurrences were counted straight from the filter words
+
 static uint4 load_chunk(const uint8_t *base, unsigned long long c)
 {
     uint4 r;
@@ -65,6 +67,32 @@ static bool run_case(const Case &t, const std::vector<long long> &truth)
             return false;
         }
         const long long p0 = (long long)(c * 16) - (long long)t.head;
+        // the packed form the kernels loop over: bit p <-> start position p of the chunk
+        const uint32_t b16 = alive ? pack_alive16(z) : 0u;
+        for (int p = 0; alive && p < 16; p++)
+            if (((b16 >> p) & 1u) != ((z[p / 4] >> (8 * (p % 4) + 7)) & 1u)) {
+                printf("pack_alive16 disagrees with the alive mask at position %d\n", p);
+                return false;
+            }
+        // count mode, needles of up to three bytes: when the anchors cover the needle, the zero bytes of the
+        // filter words ARE the occurrences (scan_long.cuh counts them without a hit path)
+        if (filter_covers_needle(t.k, t.pos, XK, t.xbs / 8u) && (XK == 0 || XK == 3) && p0 >= 0 &&
+            (unsigned long long)p0 + 16 <= end) {
+            g_exact_filter_chunks++;
+            uint32_t from_filter = 0, from_truth = 0;
+            for (int j = 0; j < 4; j++) {
+                uint32_t zz = swar_zero_exact(filter_word<WS, BSZ, K1, XK>(av, nx, lo, hi, j, fc));
+                for (; zz; zz &= zz - 1)
+                    from_filter++;
+            }
+            for (long long i : truth)
+                from_truth += (i >= p0 && i < p0 + 16);
+            if (from_filter != from_truth) {
+                printf("count from filter words %u != %u occurrences in chunk %llu (k %u pos %u XK %d)\n", from_filter,
+                       from_truth, c, t.k, t.pos, XK);
+                return false;
+            }
+        }
         for (int j = 0; alive && j < 4; j++)
             for (int b = 0; b < 4; b++)
                 if (z[j] & (0x80u << (8 * b))) {
@@ -180,6 +208,7 @@ int main(int argc, char **argv)
         checked++;
         with_match += !truth.empty();
     }
-    printf("ok: %lld cases (%lld with a match), every extra-anchor kind\n", checked, with_match);
+    printf("ok: %lld cases (%lld with a match), every extra-anchor kind; %lld chunks counted from filter words\n", checked,
+           with_match, g_exact_filter_chunks);
     return 0;
 }
