@@ -26,6 +26,10 @@
 #define SS_SERVICE_THREADS 256
 #define SS_SERVICE_MAX_BYTES ((size_t)4 << 20)
 #define SS_SERVICE_MAX_NEEDLE 64u
+// Residency: a grid is two CTAs of 256 threads per SM (the 857 KB text of the reference's benches is then one
+// pass of 16-byte loads; measured against 1 and 0.5 CTAs per SM and 512-thread CTAs, profiles/
+// r02_service_variants.txt).  The kernel is capped at 64 registers (__launch_bounds__(256, 4)), so two grids
+// -- four CTAs per SM -- are the most that can be co-resident; a third calling thread launches kernels.
 #define SS_SERVICE_MAX_PER_DEVICE 2
 #ifndef SS_SERVICE_GRID_NUM // CTAs of the resident grid = SMs * NUM / DEN
 #define SS_SERVICE_GRID_NUM 2
