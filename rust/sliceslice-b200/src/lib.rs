@@ -29,6 +29,14 @@ pub struct RawSharded {
 pub struct RawCtxHayset {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct RawBatch {
+    _p: [u8; 0],
+}
+#[repr(C)]
+pub struct RawHayset {
+    _p: [u8; 0],
+}
 
 pub const SS_B200_OK: c_int = 0;
 pub const SS_B200_E_POSITION: c_int = 1;
@@ -42,46 +50,93 @@ pub enum Exchange {
     Nccl = 2,
 }
 
-extern "C" {
-    fn ss_b200_strerror(status: c_int) -> *const c_char;
-    fn ss_b200_last_error() -> *const c_char;
-    fn ss_b200_searcher_new(needle: *const u8, len: usize, out: *mut *mut RawSearcher) -> c_int;
-    fn ss_b200_searcher_with_position(needle: *const u8, len: usize, position: usize, out: *mut *mut RawSearcher) -> c_int;
-    fn ss_b200_searcher_new_strict(needle: *const u8, len: usize, out: *mut *mut RawSearcher) -> c_int;
-    fn ss_b200_searcher_with_position_strict(needle: *const u8, len: usize, position: usize, out: *mut *mut RawSearcher) -> c_int;
-    fn ss_b200_rarest_position(needle: *const u8, len: usize, hist: *const u64, position: *mut usize) -> c_int;
-    fn ss_b200_haystack_byte_histogram(h: *const RawHaystack, sample_bytes: usize, hist: *mut u64) -> c_int;
-    fn ss_b200_searcher_free(s: *mut RawSearcher);
-    fn ss_b200_haystack_upload(host: *const u8, len: usize, out: *mut *mut RawHaystack) -> c_int;
-    fn ss_b200_haystack_from_device(dptr: *const c_void, len: usize, out: *mut *mut RawHaystack) -> c_int;
-    fn ss_b200_haystack_free(h: *mut RawHaystack);
-    fn ss_b200_search_in(s: *const RawSearcher, h: *const RawHaystack, found: *mut u8) -> c_int;
-    fn ss_b200_find_in(s: *const RawSearcher, h: *const RawHaystack, offset: *mut usize) -> c_int;
-    fn ss_b200_search_in_host(s: *const RawSearcher, host: *const u8, len: usize, found: *mut u8) -> c_int;
-    fn ss_b200_find_in_host(s: *const RawSearcher, host: *const u8, len: usize, offset: *mut usize) -> c_int;
-    fn ss_b200_thread_release() -> c_int;
-    fn ss_b200_set_sync_service(on: c_int, idle_us: c_int) -> c_int;
-    // multi-GPU context (one process, every GPU of the box)
-    fn ss_b200_ctx_create(ndev: c_int, devices: *const c_int, out: *mut *mut RawCtx) -> c_int;
-    fn ss_b200_ctx_free(ctx: *mut RawCtx);
-    fn ss_b200_ctx_device_count(ctx: *const RawCtx) -> c_int;
-    fn ss_b200_ctx_set_exchange(ctx: *mut RawCtx, kind: c_int) -> c_int;
-    fn ss_b200_sharded_upload(ctx: *const RawCtx, host: *const u8, len: usize, halo: usize, out: *mut *mut RawSharded) -> c_int;
-    fn ss_b200_sharded_from_device(ctx: *const RawCtx, dptrs: *const *const c_void, owned: *const usize,
-                                   spans: *const usize, out: *mut *mut RawSharded) -> c_int;
-    fn ss_b200_sharded_free(sh: *mut RawSharded);
-    fn ss_b200_sharded_len(sh: *const RawSharded) -> usize;
-    fn ss_b200_search_sharded(ctx: *mut RawCtx, s: *const RawSearcher, sh: *const RawSharded, found: *mut u8,
-                              global_offset: *mut usize) -> c_int;
-    fn ss_b200_find_in_host_multi(ctx: *mut RawCtx, s: *const RawSearcher, host: *const u8, len: usize,
-                                  offset: *mut usize) -> c_int;
-    fn ss_b200_search_in_host_multi(ctx: *mut RawCtx, s: *const RawSearcher, host: *const u8, len: usize,
-                                    found: *mut u8) -> c_int;
-    fn ss_b200_ctx_hayset_upload(ctx: *const RawCtx, blob: *const u8, offsets: *const u64, n: usize,
-                                 out: *mut *mut RawCtxHayset) -> c_int;
-    fn ss_b200_ctx_hayset_free(hs: *mut RawCtxHayset);
-    fn ss_b200_ctx_hayset_len(hs: *const RawCtxHayset) -> usize;
-    fn ss_b200_ctx_hayset_search(ctx: *mut RawCtx, s: *const RawSearcher, hs: *const RawCtxHayset, flags: *mut u8) -> c_int;
+use sys::*;
+
+/// Every entry point of `include/sliceslice_b200.h`, as declared there (kept in step by
+/// `tests/test_capi_cpu.py::test_rust_shim_declares_every_header_entry`).
+pub mod sys {
+    use super::{RawBatch, RawCtx, RawCtxHayset, RawHayset, RawHaystack, RawSearcher, RawSharded};
+    use std::os::raw::{c_char, c_int, c_void};
+    extern "C" {
+        pub fn ss_b200_strerror(status: c_int) -> *const c_char;
+        pub fn ss_b200_last_error() -> *const c_char;
+        pub fn ss_b200_abi_version() -> c_int;
+        pub fn ss_b200_searcher_new(needle: *const u8, len: usize, out: *mut *mut RawSearcher) -> c_int;
+        pub fn ss_b200_searcher_with_position(needle: *const u8, len: usize, position: usize, out: *mut *mut RawSearcher) -> c_int;
+        pub fn ss_b200_searcher_new_strict(needle: *const u8, len: usize, out: *mut *mut RawSearcher) -> c_int;
+        pub fn ss_b200_searcher_with_position_strict(needle: *const u8, len: usize, position: usize, out: *mut *mut RawSearcher) -> c_int;
+        pub fn ss_b200_rarest_position(needle: *const u8, len: usize, hist: *const u64, position: *mut usize) -> c_int;
+        pub fn ss_b200_searcher_new_rarest(needle: *const u8, len: usize, hist: *const u64, out: *mut *mut RawSearcher) -> c_int;
+        pub fn ss_b200_searcher_free(s: *mut RawSearcher);
+        pub fn ss_b200_searcher_needle_len(s: *const RawSearcher) -> usize;
+        pub fn ss_b200_searcher_position(s: *const RawSearcher) -> usize;
+        pub fn ss_b200_haystack_upload(host: *const u8, len: usize, out: *mut *mut RawHaystack) -> c_int;
+        pub fn ss_b200_haystack_from_device(dptr: *const c_void, len: usize, out: *mut *mut RawHaystack) -> c_int;
+        pub fn ss_b200_haystack_free(h: *mut RawHaystack);
+        pub fn ss_b200_haystack_len(h: *const RawHaystack) -> usize;
+        pub fn ss_b200_haystack_device_ptr(h: *const RawHaystack) -> *const c_void;
+        pub fn ss_b200_byte_histogram_device_async(dptr: *const c_void, len: usize, sample_bytes: usize, d_hist: *mut u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_haystack_byte_histogram(h: *const RawHaystack, sample_bytes: usize, hist: *mut u64) -> c_int;
+        pub fn ss_b200_search_in(s: *const RawSearcher, h: *const RawHaystack, found: *mut u8) -> c_int;
+        pub fn ss_b200_find_in(s: *const RawSearcher, h: *const RawHaystack, offset: *mut usize) -> c_int;
+        pub fn ss_b200_search_in_host(s: *const RawSearcher, host: *const u8, len: usize, found: *mut u8) -> c_int;
+        pub fn ss_b200_find_in_host(s: *const RawSearcher, host: *const u8, len: usize, offset: *mut usize) -> c_int;
+        pub fn ss_b200_find_in_host_multi(ctx: *mut RawCtx, s: *const RawSearcher, host: *const u8, len: usize, offset: *mut usize) -> c_int;
+        pub fn ss_b200_search_in_host_multi(ctx: *mut RawCtx, s: *const RawSearcher, host: *const u8, len: usize, found: *mut u8) -> c_int;
+        pub fn ss_b200_ctx_last_host_stats(ctx: *const RawCtx, h2d_bytes: *mut u64, chunks: *mut u64, chunk_bytes: *mut u64, mode: *mut c_int) -> c_int;
+        pub fn ss_b200_find_in_device_async(s: *const RawSearcher, dptr: *const c_void, len: usize, base_offset: u64, start_limit: usize, workspace: *mut c_void, d_result: *mut u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_count_in_device_async(s: *const RawSearcher, dptr: *const c_void, len: usize, start_limit: usize, workspace: *mut c_void, d_count: *mut u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_mailbox_create(world: c_int, d_mailbox: *mut *mut c_void) -> c_int;
+        pub fn ss_b200_mailbox_free(d_mailbox: *mut c_void) -> c_int;
+        pub fn ss_b200_ipc_export(dptr: *const c_void, handle_out: *mut u8) -> c_int;
+        pub fn ss_b200_ipc_open(handle: *const u8, dptr_out: *mut *mut c_void) -> c_int;
+        pub fn ss_b200_ipc_close(dptr: *mut c_void) -> c_int;
+        pub fn ss_b200_find_in_device_exchange_async(s: *const RawSearcher, dptr: *const c_void, len: usize, base_offset: u64, start_limit: usize, workspace: *mut c_void, mailboxes: *const *mut c_void, world: c_int, rank: c_int, seq: u64, d_result: *mut u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_ctx_create(ndev: c_int, devices: *const c_int, out: *mut *mut RawCtx) -> c_int;
+        pub fn ss_b200_ctx_free(ctx: *mut RawCtx);
+        pub fn ss_b200_ctx_device_count(ctx: *const RawCtx) -> c_int;
+        pub fn ss_b200_ctx_device(ctx: *const RawCtx, i: c_int) -> c_int;
+        pub fn ss_b200_ctx_set_exchange(ctx: *mut RawCtx, kind: c_int) -> c_int;
+        pub fn ss_b200_ctx_nccl_version(version: *mut c_int) -> c_int;
+        pub fn ss_b200_sharded_upload(ctx: *const RawCtx, host: *const u8, len: usize, halo: usize, out: *mut *mut RawSharded) -> c_int;
+        pub fn ss_b200_sharded_from_device(ctx: *const RawCtx, dptrs: *const *const c_void, owned: *const usize, spans: *const usize, out: *mut *mut RawSharded) -> c_int;
+        pub fn ss_b200_sharded_free(sh: *mut RawSharded);
+        pub fn ss_b200_sharded_len(sh: *const RawSharded) -> usize;
+        pub fn ss_b200_sharded_shard(sh: *const RawSharded, i: c_int, dptr: *mut *const c_void, start: *mut usize, owned: *mut usize, span: *mut usize) -> c_int;
+        pub fn ss_b200_search_sharded(ctx: *mut RawCtx, s: *const RawSearcher, sh: *const RawSharded, found: *mut u8, global_offset: *mut usize) -> c_int;
+        pub fn ss_b200_find_sharded(ctx: *mut RawCtx, s: *const RawSearcher, sh: *const RawSharded, offset: *mut usize) -> c_int;
+        pub fn ss_b200_ctx_hayset_upload(ctx: *const RawCtx, blob: *const u8, offsets: *const u64, n: usize, out: *mut *mut RawCtxHayset) -> c_int;
+        pub fn ss_b200_ctx_hayset_free(hs: *mut RawCtxHayset);
+        pub fn ss_b200_ctx_hayset_len(hs: *const RawCtxHayset) -> usize;
+        pub fn ss_b200_ctx_hayset_part(hs: *const RawCtxHayset, i: c_int, lo: *mut usize, hi: *mut usize) -> c_int;
+        pub fn ss_b200_ctx_hayset_search(ctx: *mut RawCtx, s: *const RawSearcher, hs: *const RawCtxHayset, flags: *mut u8) -> c_int;
+        pub fn ss_b200_search_many_async(s: *const RawSearcher, d_blob: *const c_void, d_offsets: *const u64, n_haystacks: usize, blob_len: usize, d_flags: *mut u8, workspace: *mut c_void, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_hayset_create(d_blob: *const c_void, d_offsets: *const u64, n_haystacks: usize, blob_len: usize, stream: *mut c_void, out: *mut *mut RawHayset) -> c_int;
+        pub fn ss_b200_hayset_free(hs: *mut RawHayset);
+        pub fn ss_b200_hayset_len(hs: *const RawHayset) -> usize;
+        pub fn ss_b200_hayset_search_async(s: *const RawSearcher, hs: *const RawHayset, d_flags: *mut u8, workspace: *mut c_void, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_pack_flags_async(d_flags: *const u8, n: usize, first_bit: usize, d_words: *mut u32, total_bits: usize, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_batch_create(needle_blob: *const u8, needle_off: *const u64, n_needles: usize, hay_blob: *const u8, hay_off: *const u64, n_haystacks: usize, out: *mut *mut RawBatch) -> c_int;
+        pub fn ss_b200_batch_free(b: *mut RawBatch);
+        pub fn ss_b200_batch_search_pairs(b: *const RawBatch, pair_needle: *const u32, pair_hay: *const u32, n_pairs: usize, bitmap: *mut u32, offsets: *mut u64) -> c_int;
+        pub fn ss_b200_batch_search_triangular(b: *const RawBatch, bitmap: *mut u32, matches: *mut u64) -> c_int;
+        pub fn ss_b200_batch_find_all_in(b: *const RawBatch, h: *const RawHaystack, offsets: *mut u64) -> c_int;
+        pub fn ss_b200_batch_search_pairs_async(b: *const RawBatch, d_pair_needle: *const u32, d_pair_hay: *const u32, n_pairs: usize, d_bitmap: *mut u32, d_offsets: *mut u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_batch_search_triangular_async(b: *const RawBatch, d_bitmap: *mut u32, d_matches: *mut u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_batch_find_all_in_device_async(b: *const RawBatch, dptr: *const c_void, len: usize, d_offsets: *mut u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_fill_random(d_dst: *mut c_void, len: usize, global_start: u64, seed: u64, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_fill_tiled(d_dst: *mut c_void, len: usize, global_start: u64, d_src: *const c_void, src_len: usize, stream: *mut c_void) -> c_int;
+        pub fn ss_b200_set_scan_variant(variant: c_int) -> c_int;
+        pub fn ss_b200_set_scan_tuning(ctas_per_sm: c_int, unroll: c_int, tile_kib: c_int, stages: c_int) -> c_int;
+        pub fn ss_b200_set_extra_anchors(n: c_int) -> c_int;
+        pub fn ss_b200_set_launch_pdl(on: c_int) -> c_int;
+        pub fn ss_b200_set_sync_service(on: c_int, idle_us: c_int) -> c_int;
+        pub fn ss_b200_set_host_path(mode: c_int, chunk_mib: c_int, copy_threads: c_int) -> c_int;
+        pub fn ss_b200_measure_h2d(bytes: usize, reps: c_int, gb_per_s: *mut f64) -> c_int;
+        pub fn ss_b200_thread_release() -> c_int;
+        pub fn ss_b200_thread_footprint(device_bytes: *mut usize, pinned_bytes: *mut usize) -> c_int;
+        pub fn ss_b200_launch_count() -> u64;
+    }
 }
 
 /// Synchronous searches over short device-resident haystacks go through a resident kernel (no launch per
@@ -319,4 +374,56 @@ impl Drop for Context {
     fn drop(&mut self) {
         unsafe { ss_b200_ctx_free(self.0) }
     }
+}
+
+/// Needle and haystack sets for the batched modes (the reference's two bench loops,
+/// `bench/benches/i386.rs:118-131` and `:246-257`).  Sets are given as slices of byte strings.
+pub struct Batch {
+    raw: *mut RawBatch,
+    n_needles: usize,
+}
+unsafe impl Send for Batch {}
+fn csr(items: &[&[u8]]) -> (Vec<u8>, Vec<u64>) {
+    let mut blob = Vec::new();
+    let mut off = vec![0u64];
+    for it in items {
+        blob.extend_from_slice(it);
+        off.push(blob.len() as u64);
+    }
+    (blob, off)
+}
+impl Batch {
+    pub fn new(needles: &[&[u8]], haystacks: &[&[u8]]) -> Self {
+        let (nb, no) = csr(needles);
+        let (hb, ho) = csr(haystacks);
+        let mut raw = std::ptr::null_mut();
+        check(unsafe {
+            ss_b200_batch_create(nb.as_ptr(), no.as_ptr(), needles.len(), hb.as_ptr(), ho.as_ptr(), haystacks.len(), &mut raw)
+        });
+        Batch { raw, n_needles: needles.len() }
+    }
+    /// Every needle of the batch over one device-resident haystack in a single launch: first offsets.
+    pub fn find_all_in(&self, haystack: &DeviceHaystack) -> Vec<Option<usize>> {
+        let mut out = vec![u64::MAX; self.n_needles];
+        check(unsafe { ss_b200_batch_find_all_in(self.raw, haystack.0, out.as_mut_ptr()) });
+        out.into_iter().map(|v| if v == u64::MAX { None } else { Some(v as usize) }).collect()
+    }
+    /// `needle i` in every `haystack j >= i` of one length-sorted list: (bitmap, number of matches).
+    pub fn search_triangular(&self) -> (Vec<u32>, u64) {
+        let w = self.n_needles as u64;
+        let mut bitmap = vec![0u32; ((w * (w + 1) / 2 + 31) / 32) as usize];
+        let mut matches = 0u64;
+        check(unsafe { ss_b200_batch_search_triangular(self.raw, bitmap.as_mut_ptr(), &mut matches) });
+        (bitmap, matches)
+    }
+}
+impl Drop for Batch {
+    fn drop(&mut self) {
+        unsafe { ss_b200_batch_free(self.raw) }
+    }
+}
+
+/// Kernel launches issued by the library in this process so far.
+pub fn launch_count() -> u64 {
+    unsafe { ss_b200_launch_count() }
 }

@@ -213,3 +213,21 @@ def test_thread_local_lanes_are_released_without_a_device():
     t.start()
     t.join()
     assert out == [(0, 0)]
+
+
+def test_rust_shim_declares_every_header_entry():
+    """rust/sliceslice-b200 cannot be compiled here (no rustc); what CAN be pinned is that its `sys` module
+    declares every entry point of the header, with the same number of parameters."""
+    hdr = open(os.path.join(ROOT, "include", "sliceslice_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {name: ([] if args.strip() == "void" else args.split(","))
+              for name, args in re.findall(r"\b(ss_b200_\w+)\s*\(([^;{]*?)\)\s*;", hdr)}
+    assert len(protos) >= 70
+    rs = open(os.path.join(ROOT, "rust", "sliceslice-b200", "src", "lib.rs")).read()
+    sys_block = rs[rs.index("pub mod sys {"):]
+    sys_block = sys_block[:sys_block.index("\n}\n") + 3]
+    decls = {name: ([] if not args.strip() else args.split(","))
+             for name, args in re.findall(r"pub fn (ss_b200_\w+)\(([^)]*)\)", sys_block)}
+    assert set(decls) == set(protos), sorted(set(protos) ^ set(decls))
+    for name, params in protos.items():
+        assert len(decls[name]) == len(params), name
