@@ -405,7 +405,7 @@ int ss_b200_set_sync_service(int on, int idle_us);
  *   mode          0 auto (pinned slices of up to 2 MiB per device in place, else the DMA ring), 1 always the DMA ring,
  *                 2 pinned input read in place by the direct-load kernel, 3 in place by the TMA kernel
  *   chunk_mib     0 auto (an eighth of a device's share of the slice, 4..64 MiB), else MiB per chunk
- *   copy_threads  memcpy workers that stage pageable input: -1 auto (min(7, cores-1)), 0 = hand pageable
+ *   copy_threads  memcpy workers that stage pageable input: -1 auto (min(15, cores-1)), 0 = hand pageable
  *                 memory to the driver.  Staged input goes through ONE device even in a multi-device
  *                 context: it is bound by the staging copy, not by a PCIe link */
 int ss_b200_set_host_path(int mode, int chunk_mib, int copy_threads);

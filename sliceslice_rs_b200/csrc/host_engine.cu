@@ -125,8 +125,8 @@ size_t round_up_pow2(size_t v)
 }
 
 // Chunk size: the caller's setting, else sized from the slice -- an eighth of a lane's share, between 4
-// and 64 MiB (32 MiB when staged through the pinned ring), so that a lane's ring (3 buffers) is never
-// larger than 3/8 of what it has to move and short slices do not allocate 3 x 64 MiB.
+// and 64 MiB, so that a lane's ring (3 buffers) is never larger than 3/8 of what it has to move and short
+// slices do not allocate 3 x 64 MiB.
 size_t pick_chunk(size_t len, int n_lanes, bool staged, const SsHostPathTuning &t)
 {
     size_t chunk;
@@ -135,7 +135,8 @@ size_t pick_chunk(size_t len, int n_lanes, bool staged, const SsHostPathTuning &
     } else {
         const size_t share = (len + n_lanes - 1) / n_lanes;
         chunk = round_up_pow2((share + 7) / 8);
-        const size_t lo = (size_t)4 << 20, hi = (size_t)(staged ? 32 : 64) << 20;
+        const size_t lo = (size_t)4 << 20, hi = (size_t)64 << 20;
+        (void)staged;
         chunk = chunk < lo ? lo : (chunk > hi ? hi : chunk);
     }
     if (chunk > len)
@@ -257,7 +258,10 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes_in, const ss_b200_sear
         int want = ht.copy_threads;
         if (want < 0) {
             const unsigned hc = std::thread::hardware_concurrency();
-            want = hc > 2 ? (int)(hc - 1 < 7u ? hc - 1 : 7u) : 0; // workers next to the calling thread
+            // workers next to the calling thread.  The staging memcpy is what bounds pageable input, and it
+            // scales with threads well past 8 on these hosts (2 GiB pageable, one box: 3 workers 27 GB/s,
+            // 7: 36, 11: 44, 15: 45 with 64 MiB chunks; profiles/r02_pageable_threads.txt)
+            want = hc > 2 ? (int)(hc - 1 < 15u ? hc - 1 : 15u) : 0;
         }
         if (want > 0) {
             pool_threads = CopyPool::get().ensure(want);
