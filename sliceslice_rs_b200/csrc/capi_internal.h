@@ -119,7 +119,7 @@ int ss_capi_find_on_lane(SsLane *c, const ss_b200_searcher *s, const void *dptr,
 // service.cu: the resident kernel of the synchronous short-haystack calls
 bool ss_service_eligible(const ss_b200_searcher *s, size_t len);
 int ss_service_find(SsLane *lane, const ss_b200_searcher *s, const void *dptr, size_t len, unsigned idle_us,
-                    size_t *offset, bool *used);
+                    size_t *offset, bool *used, bool mapped_host = false);
 void ss_service_release(void *service);
 void ss_capi_service_tuning(int *on, unsigned *idle_us);
 // spin on a mapped result word until the kernel behind it has written it (or its stream reports an error)

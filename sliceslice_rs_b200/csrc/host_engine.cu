@@ -239,6 +239,19 @@ int ss_host_engine_find(SsLane *const *lanes, int n_lanes_in, const ss_b200_sear
         memset(c->small_host + len, 0, 32 - (len & 15)); // the scan reads whole 16-byte chunks
         st.mode = 3;
         st.chunks = 1;
+        {
+            // through the lane's resident kernel when there is one to be had: no launch (service.cu)
+            int on = 0;
+            unsigned idle_us = 0;
+            ss_capi_service_tuning(&on, &idle_us);
+            if (on && ss_service_eligible(s, len)) {
+                SsDeviceGuard guard(c->device);
+                bool used = false;
+                int rc = ss_service_find(c, s, c->small_dev, len, idle_us, offset, &used, true);
+                if (rc != SS_B200_OK || used)
+                    return rc;
+            }
+        }
         return ss_capi_find_on_lane(c, s, c->small_dev, len, offset, 1); // direct loads, never the staged ring
     }
 

@@ -15,7 +15,9 @@
 // the next launch); every CTA also carries a watchdog, so a lost host cannot leave the GPU spinning.
 //
 // Served: first-match searches (ss_b200_find_in / ss_b200_search_in) over device memory of up to
-// SS_SERVICE_MAX_BYTES with needles of up to 64 bytes; everything else takes the launched kernels.
+// SS_SERVICE_MAX_BYTES with needles of up to 64 bytes, and short HOST slices (ss_b200_find_in_host, up to
+// 32 KiB, needles of up to 17 bytes) out of the lane's mapped pinned copy; everything else takes the
+// launched kernels.
 // Loads of the haystack bypass L1 (ld.global.cg): the grid outlives any number of host-side writes to
 // the haystack between two calls.
 #include "capi_internal.h"
@@ -41,7 +43,7 @@ struct SsServiceDesc {
     uint32_t seq0;
     uint32_t k;
     uint32_t pos;
-    uint32_t cmd; // 1 search, 2 retire now
+    uint32_t cmd; // 1 search device memory, 2 retire now, 3 search a haystack in mapped HOST memory
     uint64_t hay;
     uint64_t n;
     uint8_t needle_lo[32];
@@ -76,6 +78,18 @@ __device__ __forceinline__ uint4 ld_cg16(const uint4 *p)
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// haystack chunk: device memory through L2 (never L1: the grid outlives host-side writes); mapped host memory
+// with a volatile load, which goes to the host every time (nothing of it may linger in a GPU cache between
+// two requests -- the host rewrites that buffer before each call)
+template <bool SYS>
+__device__ __forceinline__ uint4 ld_hay16(const uint4 *p)
+{
+    if (!SYS)
+        return ld_cg16(p);
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p)
 {
     uint32_t v;
@@ -106,7 +120,7 @@ __device__ __forceinline__ unsigned long long now_ns()
 }
 
 // one request: every thread of the grid takes chunks c, c + T, c + 2T, ... (coalesced 16-byte loads)
-template <int WS, bool BSZ, bool K1>
+template <int WS, bool BSZ, bool K1, bool SYS>
 __device__ __forceinline__ void service_scan(const ScanArgs &a)
 {
     const uint4 *chunks = reinterpret_cast<const uint4 *>(a.hay - a.head);
@@ -125,14 +139,14 @@ __device__ __forceinline__ void service_scan(const ScanArgs &a)
         if (key != 0 && (long long)(c * 16ull) - (long long)a.head > (long long)~key)
             break;
         uint4 av[1], nx[1], lo[1], hi[1];
-        av[0] = ld_cg16(chunks + (c < last ? c : last));
-        nx[0] = ld_cg16(chunks + (c + 1 < last ? c + 1 : last));
+        av[0] = ld_hay16<SYS>(chunks + (c < last ? c : last));
+        nx[0] = ld_hay16<SYS>(chunks + (c + 1 < last ? c + 1 : last));
         if (K1 || q == 0) {
             lo[0] = av[0];
             hi[0] = nx[0];
         } else {
-            lo[0] = ld_cg16(chunks + (c + q < last ? c + q : last));
-            hi[0] = ld_cg16(chunks + (c + q + 1 < last ? c + q + 1 : last));
+            lo[0] = ld_hay16<SYS>(chunks + (c + q < last ? c + q : last));
+            hi[0] = ld_hay16<SYS>(chunks + (c + q + 1 < last ? c + q + 1 : last));
         }
         uint32_t fl[1];
         fl[0] = chunk_flag_x<WS, BSZ, K1, 0>(av[0], nx[0], lo[0], hi[0], fc);
@@ -285,16 +299,30 @@ __global__ void __launch_bounds__(SS_SERVICE_THREADS, 4)
         {
             const uint32_t r = sa.k == 1u ? 0u : sa.pos % 16u;
             const uint32_t cls = sa.k == 1u ? 8u : 2u * (r / 4u) + ((r % 4u) ? 1u : 0u);
-            switch (cls) {
-            case 0: service_scan<0, true, false>(sa); break;
-            case 1: service_scan<0, false, false>(sa); break;
-            case 2: service_scan<1, true, false>(sa); break;
-            case 3: service_scan<1, false, false>(sa); break;
-            case 4: service_scan<2, true, false>(sa); break;
-            case 5: service_scan<2, false, false>(sa); break;
-            case 6: service_scan<3, true, false>(sa); break;
-            case 7: service_scan<3, false, false>(sa); break;
-            default: service_scan<0, true, true>(sa); break;
+            if (s_desc[3] == 3u) { // launch-uniform: the haystack is mapped host memory (needles of up to 17 bytes)
+                switch (cls) {
+                case 0: service_scan<0, true, false, true>(sa); break;
+                case 1: service_scan<0, false, false, true>(sa); break;
+                case 2: service_scan<1, true, false, true>(sa); break;
+                case 3: service_scan<1, false, false, true>(sa); break;
+                case 4: service_scan<2, true, false, true>(sa); break;
+                case 5: service_scan<2, false, false, true>(sa); break;
+                case 6: service_scan<3, true, false, true>(sa); break;
+                case 7: service_scan<3, false, false, true>(sa); break;
+                default: service_scan<0, true, true, true>(sa); break;
+                }
+            } else {
+                switch (cls) {
+                case 0: service_scan<0, true, false, false>(sa); break;
+                case 1: service_scan<0, false, false, false>(sa); break;
+                case 2: service_scan<1, true, false, false>(sa); break;
+                case 3: service_scan<1, false, false, false>(sa); break;
+                case 4: service_scan<2, true, false, false>(sa); break;
+                case 5: service_scan<2, false, false, false>(sa); break;
+                case 6: service_scan<3, true, false, false>(sa); break;
+                case 7: service_scan<3, false, false, false>(sa); break;
+                default: service_scan<0, true, true, false>(sa); break;
+                }
             }
         }
 
@@ -448,9 +476,11 @@ bool ss_service_eligible(const ss_b200_searcher *s, size_t len)
 // One synchronous first-match search through the lane's resident kernel (created on first use).
 // SS_B200_E_ARG with *used = false when no service slot is free: the caller launches a kernel instead.
 int ss_service_find(SsLane *lane, const ss_b200_searcher *s, const void *dptr, size_t len, unsigned idle_us,
-                    size_t *offset, bool *used)
+                    size_t *offset, bool *used, bool mapped_host)
 {
     *used = false;
+    if (mapped_host && s->needle.size() > 17)
+        return SS_B200_OK; // the tail of a longer needle is compared with cached loads: launch instead
     SsService *sv = (SsService *)lane->service;
     if (!sv) {
         if (lane->device < 0 || lane->device >= 64)
@@ -497,7 +527,7 @@ int ss_service_find(SsLane *lane, const ss_b200_searcher *s, const void *dptr, s
         lane->service = sv;
     }
     unsigned long long r = 0;
-    int rc = service_roundtrip(sv, 1u, s, dptr, len, idle_us, &r);
+    int rc = service_roundtrip(sv, mapped_host ? 3u : 1u, s, dptr, len, idle_us, &r);
     if (rc != SS_B200_OK)
         return rc;
     *offset = r == SS_NONE_U64 ? SS_B200_NPOS : (size_t)r;
