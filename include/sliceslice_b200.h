@@ -152,7 +152,8 @@ int ss_b200_find_in(const ss_b200_searcher *s, const ss_b200_haystack *h, size_t
 
 /* search_in(&[u8]) with a HOST slice: the literal analogue of src/x86.rs:523.
  * A slice of up to 32 KiB (the reference's short-haystack regime) is copied into the calling thread's
- * mapped pinned buffer and scanned in place over PCIe: one launch, no DMA, no events.  Longer slices
+ * mapped pinned buffer and scanned in place over PCIe: no DMA, no events -- and, for needles of up to 17
+ * bytes, no launch either (the thread's resident kernel reads it, see ss_b200_set_sync_service).  Longer slices
  * stream to the device in chunks (a ring of three device buffers sized from the slice: an eighth of
  * it, between 4 and 64 MiB each; copy/scan overlap; the host feeds at most three chunks ahead of the
  * results it has seen, so a match stops the feeding) and are scanned there; PCIe-bound by
@@ -394,7 +395,8 @@ int ss_b200_set_extra_anchors(int n);
  * one stream overlap each launch with the previous scan): 1 = on (default), 0 = plain launches. */
 int ss_b200_set_launch_pdl(int on);
 /* Synchronous searches (ss_b200_find_in / ss_b200_search_in) over device-resident haystacks of up to
- * 4 MiB with needles of up to 64 bytes do not launch a kernel per call: a resident grid per calling thread
+ * 4 MiB with needles of up to 64 bytes (and ss_b200_find_in_host / _search_in_host over host slices of up to
+ * 32 KiB with needles of up to 17 bytes) do not launch a kernel per call: a resident grid per calling thread
  * (at most two per device) polls a request word in mapped pinned memory and answers into another, so a
  * call costs one PCIe round trip plus the scan -- the regime of the reference's per-needle loops
  * (bench/benches/i386.rs:252-256).  The grid retires by itself idle_us after the last call (default 100;
